@@ -1,0 +1,148 @@
+/* rsoptsc_b200 -- C ABI of the B200 (sm_100a) implementation of RSoptSC's cell-by-cell
+ * numerical hot path.  This is the drop-in boundary: the entry points are what an R `.Call`
+ * shim (r/rsoptsc_shim.c) binds in place of the bodies of the reference's R
+ * functions.  The reference has no native interface of its own (NAMESPACE:1-86 has no
+ * useDynLib), so every function cites the R function it replaces.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all matrices are column-major FP64 exactly as R holds them
+ *   - sizes are int64_t, indices int32_t and 0-based at this boundary (the R shim adds 1)
+ *   - every function returns 0 on success, non-zero on failure; rsoptsc_last_error() gives
+ *     the message (thread-local).  Nothing is thrown across the boundary.
+ *   - the caller owns all host buffers, the library owns all device memory
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ *   - `*_dev` variants take DEVICE pointers for the large inputs/outputs (used by bench.py to
+ *     time the path with inputs resident in HBM); the plain variants take HOST pointers and
+ *     perform the host<->device copies themselves.
+ */
+#ifndef RSOPTSC_B200_H
+#define RSOPTSC_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSOPTSC_ABI_VERSION 1
+
+/* stop codes of the ADMM (R/SimilarityM.R:134-137, :157-162, :191-194) */
+#define RSOPTSC_STOP_MAXITER 1
+#define RSOPTSC_STOP_ERRMIN 2
+#define RSOPTSC_STOP_EPSILON 3
+
+/* ---- lifecycle ------------------------------------------------------------------- */
+int rsoptsc_abi_version(void);
+/* Select the CUDA device for this process (one process per GPU) and create the stream and
+ * dense-solver handles.  device < 0 keeps the current device. */
+int rsoptsc_init(int device);
+int rsoptsc_finalize(void);
+const char* rsoptsc_last_error(void);
+/* Number of kernels of this library launched since init (bench.py's gpu_launches). */
+int64_t rsoptsc_kernel_launches(void);
+/* Device-time (ms, CUDA events on the library stream) spent in the named phase since the last
+ * rsoptsc_timers_reset(); names: "gram", "eig", "recon", "column_step", "lanczos", "dense_ew",
+ * "knn", "normalize", "pca", "symm", "nmf", "nndsvd".  Returns -1 for an unknown name. */
+double rsoptsc_phase_ms(const char* name);
+int64_t rsoptsc_phase_calls(const char* name);
+int rsoptsc_timers_reset(void);
+int rsoptsc_timers_enable(int on);
+
+/* device-memory helpers for the *_dev entry points */
+int rsoptsc_dev_alloc(void** dptr, int64_t bytes);
+int rsoptsc_dev_free(void* dptr);
+int rsoptsc_dev_upload(void* dptr, const void* host, int64_t bytes);
+int rsoptsc_dev_download(void* host, const void* dptr, int64_t bytes);
+int rsoptsc_dev_sync(void);
+
+/* ---- SimilarityM stages ---------------------------------------------------------- */
+/* a1  R/SimilarityM.R:34-39   X = column-L2-normalised (data - min)/max ; data, X: m x n */
+int rsoptsc_normalize(const double* data, int64_t m, int64_t n, double* X);
+int rsoptsc_normalize_dev(const double* d_data, int64_t m, int64_t n, double* d_X);
+
+/* a2  R/SimilarityM.R:41-72   sdev^2 of prcomp(t(X)) (min(m,n) values, descending) and K.
+ * emb (n x ncomp, column-major, may be NULL): first ncomp PCA score columns of t(X), the
+ * deterministic stand-in for Rtsne/umap. */
+int rsoptsc_pca_spectrum(const double* X, int64_t m, int64_t n, double* eig, int32_t* K,
+                         double* emb, int32_t ncomp);
+
+/* a3  R/SimilarityM.R:76-77,83-84  exact K nearest neighbours (Euclid, self included) of each
+ * row of emb (n x dim, column-major, leading dimension n) using the first `dim` columns.
+ * idx: n x K row-major (idx[j*K + t]), 0-based, ascending (distance, index). */
+int rsoptsc_knn(const double* emb, int64_t n, int32_t dim, int32_t K, int32_t* idx);
+
+/* a4-a10  computeM(D, X, lambda)  R/SimilarityM.R:115-197.
+ * Mask given as neighbour lists (row j of Z may be non-zero only in columns idx[j*K..]).
+ * Z (n x n dense, may be NULL), E = ||X - XZ||_F, iters = value of `iter` at return,
+ * stop = RSOPTSC_STOP_*, err_trace (may be NULL): 2*100 doubles, Err[i,1] at [i], Err[i,2]
+ * lower bound at [100+i] (the reference prints Err[i,1] at :190). */
+int rsoptsc_computeM(const double* X, int64_t m, int64_t n, const int32_t* idx, int32_t K,
+                     double lambda, double* Z, double* E, int32_t* iters, int32_t* stop,
+                     double* err_trace);
+/* Same with the reference's dense mask argument D (n x n, entries > 0 are forbidden). */
+int rsoptsc_computeM_dense_mask(const double* D, const double* X, int64_t m, int64_t n,
+                                double lambda, double* Z, double* E, int32_t* iters,
+                                int32_t* stop, double* err_trace);
+
+/* a11  R/SimilarityM.R:94-95   W = 0.5*(|Z'| + |Z'^T|), Z' = Z with entries <= DBL_EPSILON
+ * zeroed.  Z, W: n x n dense. */
+int rsoptsc_threshold_symmetrise(const double* Z, int64_t n, double* W);
+int rsoptsc_threshold_symmetrise_dev(const double* d_Z, int64_t n, double* d_W);
+
+/* Whole SimilarityM (R/SimilarityM.R:27-97): a1, a2, a3, a4-a10, a11.
+ *   data      m x n raw (log-normalised) expression
+ *   emb       n x emb_dim embedding (what Rtsne/umap return in the reference), or NULL to use
+ *             the in-library PCA embedding; the first 3 columns are used (quirk Q1)
+ *   K_override  > 0 forces K (config 5), 0 applies the reference rule
+ *   W         n x n dense similarity or NULL
+ *   sparse COO output (optional, all NULL to skip): *nnz_inout holds the capacity on entry
+ *             and the count on return (upper triangle incl. diagonal, 0-based)
+ *   emb_out   n x 3 embedding actually used (may be NULL) */
+int rsoptsc_similarity(const double* data, int64_t m, int64_t n, const double* emb,
+                       int32_t emb_dim, double lambda, int32_t K_override, double* W,
+                       int64_t* nnz_inout, int32_t* rows, int32_t* cols, double* vals,
+                       double* E, int32_t* iters, int32_t* K_out, double* emb_out);
+/* Device-resident variant: d_data (m x n) and d_emb (n x emb_dim or NULL) are device pointers,
+ * d_W (n x n, may be NULL) is a device pointer; scalars are host pointers. */
+int rsoptsc_similarity_dev(const double* d_data, int64_t m, int64_t n, const double* d_emb,
+                           int32_t emb_dim, double lambda, int32_t K_override, double* d_W,
+                           double* E, int32_t* iters, int32_t* K_out);
+
+/* ---- ClusterCells stages ---------------------------------------------------------- */
+/* a12-a13  NMF::nmf(V, rank=k, method='lee', seed='nndsvd') + row-argmax labels
+ * (R/Clustering.R:29-37).  V: n x n non-negative (dense).  basis: n x k, coef: k x n
+ * (either may be NULL), labels: n, 1-based like R; iters: iterations performed. */
+int rsoptsc_nmf_lee(const double* V, int64_t n, int32_t k, int32_t max_iter, double* basis,
+                    double* coef, int32_t* labels, int32_t* iters);
+int rsoptsc_nmf_lee_dev(const double* d_V, int64_t n, int32_t k, int32_t max_iter,
+                        double* basis, double* coef, int32_t* labels, int32_t* iters);
+
+/* ---- CountClusters stages --------------------------------------------------------- */
+/* a14  GetComponents(data, tol)  R/Clustering.R:96-105: ascending |eigenvalues| of the
+ * symmetric normalised Laplacian of S (n x n) and the count <= tol. */
+int rsoptsc_get_components(const double* S, int64_t n, double tol, double* vals,
+                           int32_t* n_eigs);
+/* a17  GetConsensus + truncation of GetEnsemble (R/Clustering.R:143-153, :164-175):
+ * labels: R x n row-major int32; consen: n x n; entries <= R*tau zeroed, then symmetrised. */
+int rsoptsc_consensus(const int32_t* labels, int32_t R, int64_t n, double tau, double* consen);
+/* a16  cluster::pam(P, k)$clustering (R/Clustering.R:137): P n x dim column-major;
+ * labels n (1-based, numbered by first appearance), medoids k (0-based). */
+int rsoptsc_pam(const double* P, int64_t n, int32_t dim, int32_t k, int32_t* labels,
+                int32_t* medoids);
+/* a14-a18  CountClusters(data, tol, range=lo:hi, n_comp)  R/Clustering.R:61-83.
+ * vals: n ascending eigenvalues of the consensus Laplacian (may be NULL). */
+int rsoptsc_count_clusters(const double* S, int64_t n, double tol, int32_t range_lo,
+                           int32_t range_hi, int32_t n_comp, int32_t* upper_bound,
+                           int32_t* lower_bound, double* vals, int32_t* n_eigs);
+
+/* ---- host-only helpers (no GPU needed; exercised by the CPU test-suite) ---------------- */
+/* Eigen-decomposition of a symmetric tridiagonal matrix (the small problem of every Lanczos
+ * run): d (k) diagonal in / ascending eigenvalues out, e (k-1) off-diagonal, V (k x k
+ * column-major eigenvectors, may be NULL). */
+int rsoptsc_host_tridiag_eig(int32_t k, double* d, const double* e, double* V);
+/* The K rule of R/SimilarityM.R:61-72 applied to a descending PCA spectrum of length len. */
+int32_t rsoptsc_host_choose_K(const double* eig, int64_t len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSOPTSC_B200_H */

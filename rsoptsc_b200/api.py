@@ -1,0 +1,225 @@
+"""Host-side mirror of the reference's R interface for the hot path, over the C ABI.
+
+Same function names, argument meaning and return fields as the reference
+(R/SimilarityM.R:27-28,96; R/Clustering.R:20-23,39-41,61,80-82,96-104,164), so the parity tests
+read like the reference's own tests.  Matrices are genes x cells (column-major inside the
+library, any numpy layout accepted here).  Indices/labels are 1-based like R where the reference
+returns them (labels, upper_bound); neighbour index matrices are 0-based numpy arrays.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import RsoptscError, c_double_p, c_int32_p, c_int64_p  # noqa: F401
+
+STOP_REASON = {1: "reached max iter", 2: "convergence by error min", 3: "reached epsilon"}
+
+
+def _f64(a):
+    return np.asfortranarray(np.asarray(a, dtype=np.float64))
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_int32_p)
+
+
+def normalize(data):
+    """R/SimilarityM.R:34-39."""
+    lib = _lib.init()
+    d = _f64(data)
+    m, n = d.shape
+    X = np.empty((m, n), dtype=np.float64, order="F")
+    _lib.check(lib.rsoptsc_normalize(_dp(d), m, n, _dp(X)))
+    return X
+
+
+def pca_spectrum(X, ncomp=0):
+    """R/SimilarityM.R:41-72 -> dict(eig=sdev^2, K=..., emb=n x ncomp PCA scores or None)."""
+    lib = _lib.init()
+    x = _f64(X)
+    m, n = x.shape
+    eig = np.empty(min(m, n), dtype=np.float64)
+    K = C.c_int32(0)
+    emb = np.empty((n, ncomp), dtype=np.float64, order="F") if ncomp else None
+    _lib.check(lib.rsoptsc_pca_spectrum(_dp(x), m, n, _dp(eig), C.byref(K), _dp(emb) if ncomp else None, ncomp))
+    return dict(eig=eig, K=int(K.value), emb=emb)
+
+
+def knn(emb, K, dim=3):
+    """R/SimilarityM.R:76-77 (FNN::get.knnx on the first `dim` embedding columns); 0-based n x K."""
+    lib = _lib.init()
+    e = _f64(np.asarray(emb)[:, :dim])
+    n, dim = e.shape
+    idx = np.empty((n, K), dtype=np.int32)
+    _lib.check(lib.rsoptsc_knn(_dp(e), n, dim, K, _ip(idx)))
+    return idx
+
+
+def _computeM_outputs(n, want_Z):
+    Z = np.empty((n, n), dtype=np.float64, order="F") if want_Z else None
+    return Z, C.c_double(0), C.c_int32(0), C.c_int32(0), np.zeros(200, dtype=np.float64)
+
+
+def computeM(D, X, lam, idx=None, return_Z=True):
+    """computeM(D, X, lambda) of R/SimilarityM.R:115 -> dict(Z, E, iters, stop, Err).
+    Either the reference's dense mask D (n x n, entries > 0 forbidden) or a 0-based neighbour
+    list `idx` (n x K) may be given."""
+    lib = _lib.init()
+    x = _f64(X)
+    m, n = x.shape
+    Z, E, iters, stop, trace = _computeM_outputs(n, return_Z)
+    zp = _dp(Z) if return_Z else None
+    if idx is not None:
+        ix = np.ascontiguousarray(idx, dtype=np.int32)
+        if ix.ndim != 2 or ix.shape[0] != n:
+            raise ValueError("idx must be n x K")
+        _lib.check(lib.rsoptsc_computeM(_dp(x), m, n, _ip(ix), ix.shape[1], float(lam), zp, C.byref(E),
+                                        C.byref(iters), C.byref(stop), _dp(trace)))
+    else:
+        d = _f64(D)
+        if d.shape != (n, n):
+            raise ValueError("D must be n x n")
+        _lib.check(lib.rsoptsc_computeM_dense_mask(_dp(d), _dp(x), m, n, float(lam), zp, C.byref(E),
+                                                   C.byref(iters), C.byref(stop), _dp(trace)))
+    it = int(iters.value)
+    return dict(Z=Z, E=float(E.value), iters=it, stop=STOP_REASON.get(int(stop.value), "?"),
+                Err=np.stack([trace[:100], trace[100:]], axis=1)[:max(it, 0)])
+
+
+def threshold_symmetrise(Z):
+    """R/SimilarityM.R:94-95."""
+    lib = _lib.init()
+    z = _f64(Z)
+    n = z.shape[0]
+    W = np.empty((n, n), dtype=np.float64, order="F")
+    _lib.check(lib.rsoptsc_threshold_symmetrise(_dp(z), n, _dp(W)))
+    return W
+
+
+def SimilarityM(lam=0.5, data=None, embedding=None, K=None, dense=True, sparse=False):
+    """SimilarityM(lambda, data, ...) of R/SimilarityM.R:27 -> dict(W, E, nl_embedding, ...).
+
+    `embedding` is what Rtsne/umap produce in the reference (n x >= 3); None selects the
+    deterministic in-library PCA embedding.  `K` forces the neighbour count (config 5)."""
+    lib = _lib.init()
+    d = _f64(data)
+    m, n = d.shape
+    emb = None if embedding is None else _f64(embedding)
+    W = np.empty((n, n), dtype=np.float64, order="F") if dense else None
+    E, iters, Kout = C.c_double(0), C.c_int32(0), C.c_int32(0)
+    emb_out = np.zeros((n, 3), dtype=np.float64, order="F")
+    cap = C.c_int64(2 * n * 32 if sparse else 0)
+    rows = np.empty(cap.value, dtype=np.int32) if sparse else None
+    cols = np.empty(cap.value, dtype=np.int32) if sparse else None
+    vals = np.empty(cap.value, dtype=np.float64) if sparse else None
+    _lib.check(lib.rsoptsc_similarity(
+        _dp(d), m, n, _dp(emb) if emb is not None else None, emb.shape[1] if emb is not None else 0, float(lam),
+        int(K or 0), _dp(W) if dense else None, C.byref(cap) if sparse else None,
+        _ip(rows) if sparse else None, _ip(cols) if sparse else None, _dp(vals) if sparse else None,
+        C.byref(E), C.byref(iters), C.byref(Kout), _dp(emb_out)))
+    out = dict(W=W, E=float(E.value), nl_embedding=emb_out if emb is None else emb, iters=int(iters.value),
+               K=int(Kout.value))
+    if sparse:
+        c = int(cap.value)
+        out["W_coo"] = (rows[:c].copy(), cols[:c].copy(), vals[:c].copy())
+    return out
+
+
+def nmf_lee(V, rank, max_iter=2000):
+    """NMF::nmf(V, rank, method='lee', seed='nndsvd') -> dict(W basis n x k, H coef k x n, labels, iters)."""
+    lib = _lib.init()
+    v = _f64(V)
+    n = v.shape[0]
+    if v.shape != (n, n):
+        raise ValueError("V must be square (cells x cells similarity)")
+    basis = np.empty((n, rank), dtype=np.float64, order="F")
+    coef = np.empty((rank, n), dtype=np.float64, order="F")
+    labels = np.empty(n, dtype=np.int32)
+    iters = C.c_int32(0)
+    _lib.check(lib.rsoptsc_nmf_lee(_dp(v), n, int(rank), int(max_iter), _dp(basis), _dp(coef), _ip(labels),
+                                   C.byref(iters)))
+    return dict(W=basis, H=coef, labels=labels, iters=int(iters.value))
+
+
+def GetComponents(data, tol=0.01):
+    """R/Clustering.R:96-105 -> dict(val ascending, n_eigs)."""
+    lib = _lib.init()
+    s = _f64(data)
+    n = s.shape[0]
+    vals = np.empty(n, dtype=np.float64)
+    ne = C.c_int32(0)
+    _lib.check(lib.rsoptsc_get_components(_dp(s), n, float(tol), _dp(vals), C.byref(ne)))
+    return dict(val=vals, n_eigs=int(ne.value))
+
+
+def GetConsensusEnsemble(labels, tau):
+    """Sum of GetConsensus over the label table + truncation + symmetrisation
+    (R/Clustering.R:143-153, :164-175).  labels: R x n."""
+    lib = _lib.init()
+    lab = np.ascontiguousarray(labels, dtype=np.int32)
+    R, n = lab.shape
+    out = np.empty((n, n), dtype=np.float64, order="F")
+    _lib.check(lib.rsoptsc_consensus(_ip(lab), R, n, float(tau), _dp(out)))
+    return out
+
+
+def pam(P, k):
+    """cluster::pam(P, k) -> (clustering 1-based, medoid indices 0-based)."""
+    lib = _lib.init()
+    p = _f64(P)
+    n, dim = p.shape
+    labels = np.empty(n, dtype=np.int32)
+    med = np.empty(k, dtype=np.int32)
+    _lib.check(lib.rsoptsc_pam(_dp(p), n, dim, int(k), _ip(labels), _ip(med)))
+    return labels, med
+
+
+def CountClusters(data, tol=0.01, range=(2, 20), eigengap=True, n_comp=3):
+    """R/Clustering.R:61-83 -> dict(upper_bound, lower_bound, eigs=dict(val, n_eigs))."""
+    lib = _lib.init()
+    s = _f64(data)
+    n = s.shape[0]
+    vals = np.empty(n, dtype=np.float64)
+    up, lo, ne = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    _lib.check(lib.rsoptsc_count_clusters(_dp(s), n, float(tol), int(range[0]), int(range[-1]), int(n_comp),
+                                          C.byref(up), C.byref(lo), _dp(vals), C.byref(ne)))
+    return dict(upper_bound=int(up.value), lower_bound=int(lo.value), eigs=dict(val=vals, n_eigs=int(ne.value)))
+
+
+def ClusterCells(similarityMatrix=None, n_clusters=None, n_comp=3, max_iter=2000):
+    """R/Clustering.R:20-42 -> dict(H basis n x k, labels 1-based, ensemble).  With n_clusters
+    given the reference fails on an undefined variable (quirk Q11); here ensemble is None."""
+    ensemble = None
+    if n_clusters is None:
+        ensemble = CountClusters(similarityMatrix, n_comp=n_comp)
+        n_clusters = ensemble["upper_bound"]
+    r = nmf_lee(similarityMatrix, n_clusters, max_iter=max_iter)
+    return dict(H=r["W"], labels=r["labels"], ensemble=ensemble, iters=r["iters"], coef=r["H"])
+
+
+def kernel_launches():
+    return int(_lib.load().rsoptsc_kernel_launches())
+
+
+def timers(enable=True):
+    _lib.load().rsoptsc_timers_enable(1 if enable else 0)
+    _lib.load().rsoptsc_timers_reset()
+
+
+PHASES = ["normalize", "pca", "knn", "dense_ew", "gram", "eig", "recon", "column_step", "lanczos", "symm", "nndsvd",
+          "nmf", "pam", "consensus"]
+
+
+def phase_report():
+    lib = _lib.load()
+    out = {}
+    for p in PHASES:
+        ms = lib.rsoptsc_phase_ms(p.encode())
+        if ms >= 0:
+            out[p] = dict(ms=ms, calls=int(lib.rsoptsc_phase_calls(p.encode())))
+    return out

@@ -1,0 +1,465 @@
+// extern "C" boundary of librsoptsc_b200.so (declared in include/rsoptsc_b200.h).
+// Every entry point converts C++ exceptions into a status code + thread-local message.
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/rsoptsc_b200.h"
+#include "internal.h"
+
+namespace rs {
+
+std::atomic<int64_t> g_launches{0};
+static Context g_ctx;
+static thread_local std::string g_err;
+
+void ensure_init(int dev);
+Context& ctx() {
+  if (!g_ctx.initialized) ensure_init(-1);  // lazy: current device; fails loudly without a GPU
+  return g_ctx;
+}
+
+void ensure_init(int dev) {
+  if (g_ctx.initialized && (dev < 0 || dev == g_ctx.device)) return;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    fail(6, __FILE__, __LINE__, std::string("no CUDA device available: the rsoptsc_b200 path has no CPU fallback (") +
+                                    cudaGetErrorString(e) + ")");
+  if (g_ctx.initialized) {
+    cublasDestroy(g_ctx.cublas); cusolverDnDestroy(g_ctx.cusolver); cudaStreamDestroy(g_ctx.stream);
+    g_ctx = Context();
+  }
+  if (dev < 0) RS_CUDA(cudaGetDevice(&dev));
+  RS_REQUIRE(dev < count, "device index out of range");
+  RS_CUDA(cudaSetDevice(dev));
+  g_ctx.device = dev;
+  RS_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+  RS_CUBLAS(cublasCreate(&g_ctx.cublas));
+  RS_CUBLAS(cublasSetStream(g_ctx.cublas, g_ctx.stream));
+  RS_CUSOLVER(cusolverDnCreate(&g_ctx.cusolver));
+  RS_CUSOLVER(cusolverDnSetStream(g_ctx.cusolver, g_ctx.stream));
+  cudaDeviceProp prop;
+  RS_CUDA(cudaGetDeviceProperties(&prop, dev));
+  g_ctx.sm_count = prop.multiProcessorCount;
+  g_ctx.initialized = true;
+}
+
+// ---- phase timers ---------------------------------------------------------------------
+struct PhaseRec { double ms = 0; int64_t calls = 0; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending; };
+static std::vector<std::string> g_phase_names;
+static std::vector<PhaseRec> g_phases;
+static bool g_timers_on = false;
+static int g_phase_depth = 0;
+
+static int phase_id(const char* name) {
+  for (size_t i = 0; i < g_phase_names.size(); ++i)
+    if (g_phase_names[i] == name) return (int)i;
+  g_phase_names.emplace_back(name);
+  g_phases.emplace_back();
+  return (int)g_phase_names.size() - 1;
+}
+Phase::Phase(const char* name) : id(-1) {
+  // nested phases are attributed to the outermost one only
+  if (!g_timers_on || !g_ctx.initialized || g_phase_depth++ > 0) return;
+  id = phase_id(name);
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, g_ctx.stream);
+}
+Phase::~Phase() {
+  if (!g_timers_on || !g_ctx.initialized) return;
+  --g_phase_depth;
+  if (id < 0) return;
+  cudaEventRecord(e1, g_ctx.stream);
+  g_phases[id].pending.emplace_back(e0, e1);
+  g_phases[id].calls++;
+}
+static void resolve_phases() {
+  if (!g_ctx.initialized) return;
+  cudaStreamSynchronize(g_ctx.stream);
+  for (auto& p : g_phases) {
+    for (auto& ev : p.pending) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) p.ms += ms;
+      cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+    }
+    p.pending.clear();
+  }
+}
+
+void release_dense_scratch();
+
+template <class F>
+static int guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const Error& e) {
+    g_err = e.what();
+    return e.code ? e.code : 1;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  } catch (...) {
+    g_err = "unknown error";
+    return 1;
+  }
+}
+
+}  // namespace rs
+
+using namespace rs;
+
+extern "C" {
+
+int rsoptsc_abi_version(void) { return RSOPTSC_ABI_VERSION; }
+const char* rsoptsc_last_error(void) { return g_err.c_str(); }
+int rsoptsc_init(int device) { return guarded([&] { ensure_init(device); }); }
+int rsoptsc_finalize(void) {
+  return guarded([&] {
+    if (!g_ctx.initialized) return;
+    resolve_phases();
+    release_dense_scratch();
+    cublasDestroy(g_ctx.cublas); cusolverDnDestroy(g_ctx.cusolver); cudaStreamDestroy(g_ctx.stream);
+    g_ctx = Context();
+  });
+}
+int64_t rsoptsc_kernel_launches(void) { return g_launches.load(); }
+int rsoptsc_timers_enable(int on) { g_timers_on = on != 0; return 0; }
+int rsoptsc_timers_reset(void) {
+  resolve_phases();
+  for (auto& p : g_phases) { p.ms = 0; p.calls = 0; }
+  return 0;
+}
+double rsoptsc_phase_ms(const char* name) {
+  resolve_phases();
+  for (size_t i = 0; i < g_phase_names.size(); ++i)
+    if (g_phase_names[i] == name) return g_phases[i].ms;
+  return -1.0;
+}
+int64_t rsoptsc_phase_calls(const char* name) {
+  for (size_t i = 0; i < g_phase_names.size(); ++i)
+    if (g_phase_names[i] == name) return g_phases[i].calls;
+  return -1;
+}
+
+int rsoptsc_dev_alloc(void** dptr, int64_t bytes) {
+  return guarded([&] { ctx(); RS_CUDA(cudaMalloc(dptr, (size_t)bytes)); });
+}
+int rsoptsc_dev_free(void* dptr) { return guarded([&] { RS_CUDA(cudaFree(dptr)); }); }
+int rsoptsc_dev_upload(void* dptr, const void* host, int64_t bytes) {
+  return guarded([&] {
+    RS_CUDA(cudaMemcpyAsync(dptr, host, (size_t)bytes, cudaMemcpyHostToDevice, ctx().stream));
+    RS_CUDA(cudaStreamSynchronize(ctx().stream));
+  });
+}
+int rsoptsc_dev_download(void* host, const void* dptr, int64_t bytes) {
+  return guarded([&] {
+    RS_CUDA(cudaMemcpyAsync(host, dptr, (size_t)bytes, cudaMemcpyDeviceToHost, ctx().stream));
+    RS_CUDA(cudaStreamSynchronize(ctx().stream));
+  });
+}
+int rsoptsc_dev_sync(void) { return guarded([&] { RS_CUDA(cudaStreamSynchronize(ctx().stream)); }); }
+
+// ---- a1 ---------------------------------------------------------------------------------
+int rsoptsc_normalize_dev(const double* d_data, int64_t m, int64_t n, double* d_X) {
+  return guarded([&] {
+    RS_REQUIRE(m > 0 && n > 0, "normalize: empty matrix");
+    normalize_columns(d_data, m, n, d_X);
+    RS_CUDA(cudaStreamSynchronize(ctx().stream));
+  });
+}
+int rsoptsc_normalize(const double* data, int64_t m, int64_t n, double* X) {
+  return guarded([&] {
+    RS_REQUIRE(m > 0 && n > 0, "normalize: empty matrix");
+    cudaStream_t s = ctx().stream;
+    DevBuf<double> d((size_t)m * n), x((size_t)m * n);
+    d.upload(data, (size_t)m * n, s);
+    normalize_columns(d.p, m, n, x.p);
+    x.download(X, (size_t)m * n, s);
+    RS_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+// ---- a2 ---------------------------------------------------------------------------------
+int rsoptsc_pca_spectrum(const double* X, int64_t m, int64_t n, double* eig, int32_t* K, double* emb,
+                         int32_t ncomp) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    DevBuf<double> x((size_t)m * n), e;
+    x.upload(X, (size_t)m * n, s);
+    if (emb && ncomp > 0) e.alloc((size_t)n * ncomp);
+    std::vector<double> ev;
+    pca_spectrum(x.p, m, n, ev, e.p, emb ? ncomp : 0);
+    if (eig) std::memcpy(eig, ev.data(), sizeof(double) * ev.size());
+    if (K) *K = choose_K(ev);
+    if (e.p) { e.download(emb, (size_t)n * ncomp, s); RS_CUDA(cudaStreamSynchronize(s)); }
+  });
+}
+
+// ---- a3 ---------------------------------------------------------------------------------
+int rsoptsc_knn(const double* emb, int64_t n, int32_t dim, int32_t K, int32_t* idx) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(n > 0, "knn: empty embedding");
+    DevBuf<double> e((size_t)n * dim);
+    DevBuf<int32_t> out((size_t)n * K);
+    e.upload(emb, (size_t)n * dim, s);
+    knn_bruteforce(e.p, n, n, dim, K, out.p);
+    out.download(idx, (size_t)n * K, s);
+    RS_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+// ---- a4-a10 -----------------------------------------------------------------------------
+static void computeM_common(const double* X, int64_t m, int64_t n, Support& sup, double lambda, double* Z, double* E,
+                            int32_t* iters, int32_t* stop, double* err_trace) {
+  cudaStream_t s = ctx().stream;
+  DevBuf<double> x((size_t)m * n);
+  x.upload(X, (size_t)m * n, s);
+  AdmmState st;
+  AdmmResult res;
+  run_admm(x.p, m, n, sup, lambda, st, res);
+  if (Z) {
+    DevBuf<double> zd((size_t)n * n);
+    scatter_support_dense(sup, st.Zs.p, zd.p);
+    zd.download(Z, (size_t)n * n, s);
+    RS_CUDA(cudaStreamSynchronize(s));
+  }
+  if (E) *E = res.E;
+  if (iters) *iters = res.iters;
+  if (stop) *stop = res.stop;
+  if (err_trace)
+    for (int i = 0; i < 100; ++i) { err_trace[i] = res.err1[i]; err_trace[100 + i] = res.err2[i]; }
+}
+int rsoptsc_computeM(const double* X, int64_t m, int64_t n, const int32_t* idx, int32_t K, double lambda, double* Z,
+                     double* E, int32_t* iters, int32_t* stop, double* err_trace) {
+  return guarded([&] {
+    ctx();
+    RS_REQUIRE(m > 0 && n > 0, "computeM: empty matrix");
+    Support sup;
+    build_support_from_idx(sup, idx, n, K);
+    computeM_common(X, m, n, sup, lambda, Z, E, iters, stop, err_trace);
+  });
+}
+int rsoptsc_computeM_dense_mask(const double* D, const double* X, int64_t m, int64_t n, double lambda, double* Z,
+                                double* E, int32_t* iters, int32_t* stop, double* err_trace) {
+  return guarded([&] {
+    ctx();
+    RS_REQUIRE(m > 0 && n > 0, "computeM: empty matrix");
+    Support sup;
+    build_support_from_dense_mask(sup, D, n);
+    computeM_common(X, m, n, sup, lambda, Z, E, iters, stop, err_trace);
+  });
+}
+
+// ---- a11 --------------------------------------------------------------------------------
+int rsoptsc_threshold_symmetrise_dev(const double* d_Z, int64_t n, double* d_W) {
+  return guarded([&] {
+    RS_REQUIRE(n > 0, "symmetrise: empty matrix");
+    threshold_symmetrise_dense(d_Z, n, d_W);
+    RS_CUDA(cudaStreamSynchronize(ctx().stream));
+  });
+}
+int rsoptsc_threshold_symmetrise(const double* Z, int64_t n, double* W) {
+  return guarded([&] {
+    RS_REQUIRE(n > 0, "symmetrise: empty matrix");
+    cudaStream_t s = ctx().stream;
+    DevBuf<double> z((size_t)n * n), w((size_t)n * n);
+    z.upload(Z, (size_t)n * n, s);
+    threshold_symmetrise_dense(z.p, n, w.p);
+    w.download(W, (size_t)n * n, s);
+    RS_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+// ---- SimilarityM ------------------------------------------------------------------------
+struct SimOut {
+  Support sup;
+  AdmmState st;
+  AdmmResult res;
+  int K = 0;
+  DevBuf<double> emb;  // n x 3 when computed in-library
+};
+static void similarity_core(const double* d_data, int64_t m, int64_t n, const double* d_emb, int emb_dim,
+                            double lambda, int K_override, SimOut& out, DevBuf<double>& X) {
+  cudaStream_t s = ctx().stream;
+  RS_REQUIRE(m > 0 && n > 1, "similarity: need a genes x cells matrix with at least 2 cells");
+  X.alloc((size_t)m * n);
+  normalize_columns(d_data, m, n, X.p);                       // a1
+  std::vector<double> eig;
+  const bool own_emb = d_emb == nullptr;
+  const int ncomp = 3;                                        // No_Comps1 (quirk Q1)
+  if (own_emb) out.emb.alloc((size_t)n * ncomp);
+  pca_spectrum(X.p, m, n, eig, own_emb ? out.emb.p : nullptr, own_emb ? std::min<int64_t>(ncomp, std::min(m, n)) : 0);  // a2
+  out.K = K_override > 0 ? K_override : choose_K(eig);
+  out.K = (int)std::min<int64_t>(out.K, n);
+  const double* e = own_emb ? out.emb.p : d_emb;
+  const int dim = own_emb ? (int)std::min<int64_t>(ncomp, std::min(m, n)) : std::min(emb_dim, ncomp);
+  RS_REQUIRE(dim >= 1, "similarity: embedding needs at least one column");
+  DevBuf<int32_t> idx((size_t)n * out.K);
+  knn_bruteforce(e, n, n, dim, out.K, idx.p);                 // a3
+  std::vector<int32_t> h_idx((size_t)n * out.K);
+  idx.download(h_idx.data(), h_idx.size(), s);
+  RS_CUDA(cudaStreamSynchronize(s));
+  build_support_from_idx(out.sup, h_idx.data(), n, out.K);
+  run_admm(X.p, m, n, out.sup, lambda, out.st, out.res);      // a4-a10
+}
+
+int rsoptsc_similarity_dev(const double* d_data, int64_t m, int64_t n, const double* d_emb, int32_t emb_dim,
+                           double lambda, int32_t K_override, double* d_W, double* E, int32_t* iters,
+                           int32_t* K_out) {
+  return guarded([&] {
+    ctx();
+    SimOut out;
+    DevBuf<double> X;
+    similarity_core(d_data, m, n, d_emb, emb_dim, lambda, K_override, out, X);
+    if (d_W) threshold_symmetrise_sparse(out.sup, out.st.Zs.p, d_W);  // a11
+    RS_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (E) *E = out.res.E;
+    if (iters) *iters = out.res.iters;
+    if (K_out) *K_out = out.K;
+  });
+}
+
+int rsoptsc_similarity(const double* data, int64_t m, int64_t n, const double* emb, int32_t emb_dim, double lambda,
+                       int32_t K_override, double* W, int64_t* nnz_inout, int32_t* rows, int32_t* cols, double* vals,
+                       double* E, int32_t* iters, int32_t* K_out, double* emb_out) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(m > 0 && n > 1, "similarity: need a genes x cells matrix with at least 2 cells");
+    DevBuf<double> d((size_t)m * n), e;
+    d.upload(data, (size_t)m * n, s);
+    if (emb) { e.alloc((size_t)n * emb_dim); e.upload(emb, (size_t)n * emb_dim, s); }
+    SimOut out;
+    DevBuf<double> X;
+    similarity_core(d.p, m, n, emb ? e.p : nullptr, emb_dim, lambda, K_override, out, X);
+    if (W) {
+      DevBuf<double> w((size_t)n * n);
+      threshold_symmetrise_sparse(out.sup, out.st.Zs.p, w.p);   // a11
+      w.download(W, (size_t)n * n, s);
+      RS_CUDA(cudaStreamSynchronize(s));
+    }
+    if (nnz_inout && rows && cols && vals) {
+      // sparse W (upper triangle incl. diagonal): assembled from the n*K support values
+      std::vector<double> zs(out.sup.nnz);
+      out.st.Zs.download(zs.data(), zs.size(), s);
+      RS_CUDA(cudaStreamSynchronize(s));
+      const auto& rp = out.sup.h_rowptr;
+      const auto& cl = out.sup.h_col;
+      auto find = [&](int i, int j) -> int64_t {  // CSR position of (i,j) or -1
+        const int* b = cl.data() + rp[i];
+        const int* en = cl.data() + rp[i + 1];
+        const int* it = std::lower_bound(b, en, j);
+        return (it == en || *it != j) ? -1 : (int64_t)(it - cl.data());
+      };
+      auto thr = [&](int64_t pos) -> double {  // thresholded |Z| at a CSR position
+        if (pos < 0) return 0.0;
+        const double z = zs[pos];
+        return z <= 2.220446049250313e-16 ? 0.0 : z;
+      };
+      int64_t cap = *nnz_inout, cnt = 0;
+      for (int64_t i = 0; i < n; ++i)
+        for (int p = rp[i]; p < rp[i + 1]; ++p) {
+          const int j = cl[p];
+          const int64_t mirror = i == j ? p : find(j, (int)i);
+          if (j < i && mirror >= 0) continue;  // the (j,i) entry (upper triangle) emits this pair
+          const double a = thr(p);
+          const double b = thr(mirror);
+          const double w = 0.5 * (a + b);
+          if (w == 0.0) continue;
+          if (cnt < cap) { rows[cnt] = (int32_t)std::min<int64_t>(i, j); cols[cnt] = (int32_t)std::max<int64_t>(i, j); vals[cnt] = w; }
+          ++cnt;
+        }
+      *nnz_inout = cnt;
+      RS_REQUIRE(cnt <= cap, "similarity: sparse output capacity too small (required count returned in nnz)");
+    }
+    if (emb_out) {
+      if (out.emb.p) { out.emb.download(emb_out, (size_t)n * 3, s); RS_CUDA(cudaStreamSynchronize(s)); }
+      else if (emb) std::memcpy(emb_out, emb, sizeof(double) * n * std::min(emb_dim, 3));
+    }
+    if (E) *E = out.res.E;
+    if (iters) *iters = out.res.iters;
+    if (K_out) *K_out = out.K;
+  });
+}
+
+// ---- a12-a13 ----------------------------------------------------------------------------
+int rsoptsc_nmf_lee_dev(const double* d_V, int64_t n, int32_t k, int32_t max_iter, double* basis, double* coef,
+                        int32_t* labels, int32_t* iters) {
+  return guarded([&] {
+    ctx();
+    NmfResult r;
+    nmf_lee(d_V, n, k, max_iter, basis, coef, labels, r);
+    if (iters) *iters = r.iters;
+  });
+}
+int rsoptsc_nmf_lee(const double* V, int64_t n, int32_t k, int32_t max_iter, double* basis, double* coef,
+                    int32_t* labels, int32_t* iters) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(n > 0, "nmf: empty matrix");
+    DevBuf<double> v((size_t)n * n);
+    v.upload(V, (size_t)n * n, s);
+    NmfResult r;
+    nmf_lee(v.p, n, k, max_iter, basis, coef, labels, r);
+    if (iters) *iters = r.iters;
+  });
+}
+
+// ---- a14-a18 ----------------------------------------------------------------------------
+int rsoptsc_get_components(const double* S, int64_t n, double tol, double* vals, int32_t* n_eigs) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(n > 0, "get_components: empty matrix");
+    DevBuf<double> d((size_t)n * n);
+    d.upload(S, (size_t)n * n, s);
+    get_components(d.p, n, tol, vals, n_eigs);
+  });
+}
+int rsoptsc_consensus(const int32_t* labels, int32_t R, int64_t n, double tau, double* consen) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(n > 0 && R > 0, "consensus: empty label table");
+    DevBuf<int32_t> l((size_t)R * n);
+    DevBuf<double> c((size_t)n * n);
+    l.upload(labels, (size_t)R * n, s);
+    consensus_dense(l.p, R, n, tau, c.p);
+    c.download(consen, (size_t)n * n, s);
+    RS_CUDA(cudaStreamSynchronize(s));
+  });
+}
+int rsoptsc_pam(const double* P, int64_t n, int32_t dim, int32_t k, int32_t* labels, int32_t* medoids) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(n > 0 && dim > 0, "pam: empty input");
+    DevBuf<double> p((size_t)n * dim);
+    p.upload(P, (size_t)n * dim, s);
+    pam(p.p, n, dim, k, labels, medoids);
+  });
+}
+int rsoptsc_count_clusters(const double* S, int64_t n, double tol, int32_t range_lo, int32_t range_hi, int32_t n_comp,
+                           int32_t* upper_bound, int32_t* lower_bound, double* vals, int32_t* n_eigs) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(n > 0, "count_clusters: empty matrix");
+    DevBuf<double> d((size_t)n * n);
+    d.upload(S, (size_t)n * n, s);
+    count_clusters(d.p, n, tol, range_lo, range_hi, n_comp, upper_bound, lower_bound, vals, n_eigs);
+  });
+}
+
+int rsoptsc_host_tridiag_eig(int32_t k, double* d, const double* e, double* V) {
+  return guarded([&] {
+    RS_REQUIRE(k >= 1, "tridiag_eig: k must be positive");
+    std::vector<double> dd(d, d + k), ee(e, e + std::max(0, k - 1)), vv;
+    tridiag_eig(dd, ee, V ? &vv : nullptr);
+    std::memcpy(d, dd.data(), sizeof(double) * k);
+    if (V) std::memcpy(V, vv.data(), sizeof(double) * (size_t)k * k);
+  });
+}
+int32_t rsoptsc_host_choose_K(const double* eig, int64_t len) {
+  std::vector<double> v(eig, eig + len);
+  return choose_K(v);
+}
+
+}  // extern "C"

@@ -1,0 +1,279 @@
+// Dense / support-indexed elementwise kernels of the SimilarityM path (HBM-bound stages):
+//   a1  column normalisation            R/SimilarityM.R:34-39
+//   A = Z - Y3/mu, Y3 += mu (Z - J)     R/SimilarityM.R:142,187
+//   a11 threshold + symmetrise          R/SimilarityM.R:94-95
+// All matrices are column-major FP64.  Reductions are two-stage with a fixed order so that
+// results are run-to-run deterministic.
+#include "internal.h"
+
+namespace rs {
+
+static constexpr int RED_BLOCKS = 592;  // 4 x 148 SMs
+static constexpr int RED_THREADS = 256;
+
+// ---- deterministic reductions -------------------------------------------------------
+struct RedScratch {
+  DevBuf<double> partial, result;
+  void ensure() {
+    if (!partial.p) { partial.alloc(RED_BLOCKS * 2); result.alloc(2); }
+  }
+};
+static RedScratch& red() {
+  static RedScratch r;
+  r.ensure();
+  return r;
+}
+void release_dense_scratch() { red().partial.release(); red().result.release(); }
+
+__global__ void k_final_sum(const double* __restrict__ partial, int count, double* __restrict__ out) {
+  __shared__ double sm[RED_THREADS / 32 + 1];
+  double v = 0;
+  for (int i = threadIdx.x; i < count; i += RED_THREADS) v += partial[i];
+  v = block_sum<RED_THREADS>(v, sm);
+  if (threadIdx.x == 0) out[0] = v;
+}
+
+static double finish_sum(int nblocks) {
+  RS_LAUNCH(k_final_sum, 1, RED_THREADS, 0, red().partial.p, nblocks, red().result.p);
+  double h = 0;
+  RS_CUDA(cudaMemcpyAsync(&h, red().result.p, sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+  RS_CUDA(cudaStreamSynchronize(ctx().stream));
+  return h;
+}
+
+__global__ void k_frob2(const double* __restrict__ a, int64_t count, double* __restrict__ partial) {
+  __shared__ double sm[RED_THREADS / 32 + 1];
+  double v = 0;
+  const int64_t stride = (int64_t)gridDim.x * RED_THREADS;
+  for (int64_t i = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < count; i += stride) {
+    const double x = a[i];
+    v += x * x;
+  }
+  v = block_sum<RED_THREADS>(v, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = v;
+}
+
+double frob2(const double* d_a, int64_t count) {
+  Phase ph("dense_ew");
+  RS_LAUNCH(k_frob2, RED_BLOCKS, RED_THREADS, 0, d_a, count, red().partial.p);
+  return finish_sum(RED_BLOCKS);
+}
+
+// ---- a1: normalisation ---------------------------------------------------------------
+__global__ void k_minmax(const double* __restrict__ a, int64_t count, double* __restrict__ pmin,
+                         double* __restrict__ pmax) {
+  __shared__ double smn[RED_THREADS / 32], smx[RED_THREADS / 32];
+  double mn = INFINITY, mx = -INFINITY;
+  const int64_t stride = (int64_t)gridDim.x * RED_THREADS;
+  for (int64_t i = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < count; i += stride) {
+    const double x = a[i];
+    mn = fmin(mn, x);
+    mx = fmax(mx, x);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < RED_THREADS / 32; ++w) { mn = fmin(mn, smn[w]); mx = fmax(mx, smx[w]); }
+    pmin[blockIdx.x] = mn;
+    pmax[blockIdx.x] = mx;
+  }
+}
+__global__ void k_minmax_final(const double* __restrict__ pmin, const double* __restrict__ pmax, int count,
+                               double* __restrict__ out) {
+  if (threadIdx.x == 0) {
+    double mn = INFINITY, mx = -INFINITY;
+    for (int i = 0; i < count; ++i) { mn = fmin(mn, pmin[i]); mx = fmax(mx, pmax[i]); }
+    out[0] = mn;
+    out[1] = mx - mn;  // max(data - min)
+  }
+}
+// One CTA per column: x = ((d - mn) / mx) / ||.||_2   (two passes over the column, 2nd from cache)
+__global__ void k_normalize_cols(const double* __restrict__ data, int64_t m, const double* __restrict__ mnmx,
+                                 double* __restrict__ X) {
+  __shared__ double sm[RED_THREADS / 32 + 1];
+  const double mn = mnmx[0], mx = mnmx[1];
+  const double* src = data + (int64_t)blockIdx.x * m;
+  double* dst = X + (int64_t)blockIdx.x * m;
+  double acc = 0;
+  for (int64_t i = threadIdx.x; i < m; i += RED_THREADS) {
+    const double x = (src[i] - mn) / mx;
+    acc += x * x;
+  }
+  const double nrm = sqrt(block_sum<RED_THREADS>(acc, sm));
+  for (int64_t i = threadIdx.x; i < m; i += RED_THREADS) dst[i] = ((src[i] - mn) / mx) / nrm;
+}
+
+void normalize_columns(const double* d_data, int64_t m, int64_t n, double* d_X) {
+  Phase ph("normalize");
+  double* part = red().partial.p;
+  RS_LAUNCH(k_minmax, RED_BLOCKS, RED_THREADS, 0, d_data, m * n, part, part + RED_BLOCKS);
+  RS_LAUNCH(k_minmax_final, 1, 32, 0, part, part + RED_BLOCKS, RED_BLOCKS, red().result.p);
+  RS_LAUNCH(k_normalize_cols, (unsigned)n, RED_THREADS, 0, d_data, m, red().result.p, d_X);
+}
+
+// ---- A = Z - Y3/mu -------------------------------------------------------------------
+__global__ void k_scale_neg(const double* __restrict__ y3, double mu, int64_t count, double* __restrict__ a) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 2;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i + 1 < count; i += stride) {
+    const double2 v = *reinterpret_cast<const double2*>(y3 + i);
+    *reinterpret_cast<double2*>(a + i) = make_double2(-(v.x / mu), -(v.y / mu));
+  }
+  if ((count & 1) && blockIdx.x == 0 && threadIdx.x == 0) a[count - 1] = -(y3[count - 1] / mu);
+}
+__global__ void k_scatter_add(const int* __restrict__ rowof, const int* __restrict__ col, const double* __restrict__ zs,
+                              int64_t nnz, int64_t n, double scale, double* __restrict__ a) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nnz) a[(int64_t)rowof[p] + (int64_t)col[p] * n] += scale * zs[p];
+}
+
+double build_A(const Support& s, const double* d_Zs, const double* d_Y3, double mu, double* d_A) {
+  Phase ph("dense_ew");
+  const int64_t nn = s.n * s.n;
+  RS_LAUNCH(k_scale_neg, RED_BLOCKS * 2, 256, 0, d_Y3, mu, nn, d_A);
+  if (s.nnz) RS_LAUNCH(k_scatter_add, cdiv(s.nnz, 256), 256, 0, s.rowof.p, s.col.p, d_Zs, s.nnz, s.n, 1.0, d_A);
+  RS_LAUNCH(k_frob2, RED_BLOCKS, RED_THREADS, 0, d_A, nn, red().partial.p);
+  return finish_sum(RED_BLOCKS);
+}
+
+// ---- q[p] = Zs - J + Y3/mu on the support -------------------------------------------
+__global__ void k_gather_term(const int* __restrict__ rowof, const int* __restrict__ col, const double* __restrict__ zs,
+                              const double* __restrict__ J, const double* __restrict__ y3, double mu, int64_t nnz,
+                              int64_t n, double* __restrict__ q) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nnz) return;
+  const int64_t off = (int64_t)rowof[p] + (int64_t)col[p] * n;
+  const double j = J ? J[off] : 0.0;
+  q[p] = zs[p] - j + y3[off] / mu;
+}
+void gather_support_term(const Support& s, const double* d_Zs, const double* d_J, const double* d_Y3, double mu,
+                         double* d_q) {
+  Phase ph("dense_ew");
+  if (s.nnz)
+    RS_LAUNCH(k_gather_term, cdiv(s.nnz, 256), 256, 0, s.rowof.p, s.col.p, d_Zs, d_J, d_Y3, mu, s.nnz, s.n, d_q);
+}
+
+// ---- Y3 += mu (Z - J) ------------------------------------------------------------------
+__global__ void k_y3_sub_J(const double* __restrict__ J, double mu, int64_t count, double* __restrict__ y3,
+                           double* __restrict__ partial) {
+  __shared__ double sm[RED_THREADS / 32 + 1];
+  double acc = 0;
+  const int64_t stride = (int64_t)gridDim.x * RED_THREADS * 2;
+  for (int64_t i = ((int64_t)blockIdx.x * RED_THREADS + threadIdx.x) * 2; i + 1 < count; i += stride) {
+    const double2 j = *reinterpret_cast<const double2*>(J + i);
+    double2 y = *reinterpret_cast<double2*>(y3 + i);
+    y.x -= mu * j.x;
+    y.y -= mu * j.y;
+    *reinterpret_cast<double2*>(y3 + i) = y;
+    acc += j.x * j.x + j.y * j.y;
+  }
+  if ((count & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const double j = J[count - 1];
+    y3[count - 1] -= mu * j;
+    acc += j * j;
+  }
+  acc = block_sum<RED_THREADS>(acc, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+// sparse part: Y3[i,j] += mu*Zs ; partial sums of (Zs-J)^2 - J^2 over the support
+__global__ void k_y3_add_Z(const int* __restrict__ rowof, const int* __restrict__ col, const double* __restrict__ zs,
+                           const double* __restrict__ J, double mu, int64_t nnz, int64_t n, double* __restrict__ y3,
+                           double* __restrict__ partial) {
+  __shared__ double sm[RED_THREADS / 32 + 1];
+  double acc = 0;
+  const int64_t stride = (int64_t)gridDim.x * RED_THREADS;
+  for (int64_t p = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x; p < nnz; p += stride) {
+    const int64_t off = (int64_t)rowof[p] + (int64_t)col[p] * n;
+    const double z = zs[p];
+    const double j = J ? J[off] : 0.0;
+    y3[off] += mu * z;
+    acc += (z - j) * (z - j) - j * j;
+  }
+  acc = block_sum<RED_THREADS>(acc, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+double update_Y3(const Support& s, const double* d_Zs, const double* d_J, double mu, double* d_Y3) {
+  Phase ph("dense_ew");
+  const int64_t nn = s.n * s.n;
+  double total = 0;
+  // order matters: the sparse kernel reads J on the support, so it may run after the dense one
+  if (d_J) {
+    RS_LAUNCH(k_y3_sub_J, RED_BLOCKS, RED_THREADS, 0, d_J, mu, nn, d_Y3, red().partial.p);
+    total += finish_sum(RED_BLOCKS);
+  }
+  const int blocks = 148;
+  RS_LAUNCH(k_y3_add_Z, blocks, RED_THREADS, 0, s.rowof.p, s.col.p, d_Zs, d_J, mu, s.nnz, s.n, d_Y3, red().partial.p);
+  total += finish_sum(blocks);
+  return total > 0 ? total : 0.0;
+}
+
+// ---- T[:, c] *= scale[c] --------------------------------------------------------------
+__global__ void k_scale_columns(double* __restrict__ T, int64_t rows, const double* __restrict__ scale) {
+  const double sc = scale[blockIdx.y];
+  double* colp = T + (int64_t)blockIdx.y * rows;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x)
+    colp[i] *= sc;
+}
+void scale_columns(double* d_T, int64_t rows, int64_t cols, const double* d_scale) {
+  if (!cols) return;
+  RS_REQUIRE(cols <= 65535 * 64, "scale_columns: too many columns");
+  // gridDim.y <= 65535: loop in slabs
+  for (int64_t c0 = 0; c0 < cols; c0 += 65535) {
+    const int64_t nc = cols - c0 < 65535 ? cols - c0 : 65535;
+    dim3 grid((unsigned)std::min<int64_t>(cdiv(rows, 256), 8), (unsigned)nc);
+    RS_LAUNCH(k_scale_columns, grid, 256, 0, d_T + c0 * rows, rows, d_scale + c0);
+  }
+}
+
+// ---- a11: threshold + symmetrise --------------------------------------------------------
+__device__ __forceinline__ double thr_abs(double z) { return z <= 2.220446049250313e-16 ? 0.0 : fabs(z); }
+
+// Tiled transpose-add: each 32x32 tile of W reads the tile of Z at (bi,bj) straight and the
+// tile at (bj,bi) through shared memory.  HBM: 16 n^2 B read + 8 n^2 B written.
+__global__ void k_symmetrise_dense(const double* __restrict__ Z, int64_t n, double* __restrict__ W) {
+  __shared__ double tile[32][33];
+  const int64_t i0 = (int64_t)blockIdx.x * 32, j0 = (int64_t)blockIdx.y * 32;
+  // load transposed partner tile: rows j0.., cols i0..
+  for (int c = threadIdx.y; c < 32; c += blockDim.y) {
+    const int64_t r = j0 + threadIdx.x, cc = i0 + c;
+    tile[c][threadIdx.x] = (r < n && cc < n) ? thr_abs(Z[r + cc * n]) : 0.0;
+  }
+  __syncthreads();
+  for (int c = threadIdx.y; c < 32; c += blockDim.y) {
+    const int64_t r = i0 + threadIdx.x, cc = j0 + c;
+    if (r < n && cc < n) W[r + cc * n] = 0.5 * (thr_abs(Z[r + cc * n]) + tile[threadIdx.x][c]);
+  }
+}
+void threshold_symmetrise_dense(const double* d_Z, int64_t n, double* d_W) {
+  Phase ph("symm");
+  dim3 grid((unsigned)cdiv(n, 32), (unsigned)cdiv(n, 32)), block(32, 8);
+  RS_LAUNCH(k_symmetrise_dense, grid, block, 0, d_Z, n, d_W);
+}
+
+__global__ void k_symmetrise_sparse(const int* __restrict__ rowof, const int* __restrict__ col,
+                                    const double* __restrict__ zs, int64_t nnz, int64_t n, double* __restrict__ W) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nnz) return;
+  const double h = 0.5 * thr_abs(zs[p]);
+  if (h == 0.0) return;
+  const int64_t i = rowof[p], j = col[p];
+  // each W entry receives at most two addends (from (i,j) and (j,i)): order-independent
+  atomicAdd(&W[i + j * n], h);
+  atomicAdd(&W[j + i * n], h);
+}
+void threshold_symmetrise_sparse(const Support& s, const double* d_Zs, double* d_W) {
+  Phase ph("symm");
+  RS_CUDA(cudaMemsetAsync(d_W, 0, sizeof(double) * s.n * s.n, ctx().stream));
+  if (s.nnz) RS_LAUNCH(k_symmetrise_sparse, cdiv(s.nnz, 256), 256, 0, s.rowof.p, s.col.p, d_Zs, s.nnz, s.n, d_W);
+}
+void scatter_support_dense(const Support& s, const double* d_Zs, double* d_Z) {
+  Phase ph("symm");
+  RS_CUDA(cudaMemsetAsync(d_Z, 0, sizeof(double) * s.n * s.n, ctx().stream));
+  if (s.nnz) RS_LAUNCH(k_scatter_add, cdiv(s.nnz, 256), 256, 0, s.rowof.p, s.col.p, d_Zs, s.nnz, s.n, 1.0, d_Z);
+}
+
+}  // namespace rs

@@ -1,0 +1,412 @@
+// a14-a18: CountClusters (R/Clustering.R:61-175): Laplacian spectrum (GetComponents), PCA + PAM
+// ensemble (GetEnsemble), consensus matrix (GetConsensus) and the eigengap rule.
+#include <algorithm>
+#include <cmath>
+
+#include "internal.h"
+#include "lanczos.h"
+
+namespace rs {
+
+static constexpr int ET = 256;
+
+// ---- a14: GetComponents ----------------------------------------------------------------------
+__global__ void k_fill_ones(double* __restrict__ v, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * ET + threadIdx.x;
+  if (i < n) v[i] = 1.0;
+}
+__global__ void k_inv_sqrt(double* __restrict__ d, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * ET + threadIdx.x;
+  if (i < n) d[i] = 1.0 / sqrt(d[i]);
+}
+// L = I - (dd_i * S_ij) * dd_j      (R/Clustering.R:99-101; sqrtm/solve of a diagonal matrix, quirk Q13)
+__global__ void k_laplacian(const double* __restrict__ S, const double* __restrict__ dd, int64_t n,
+                            double* __restrict__ L) {
+  const int64_t j = blockIdx.y;
+  const double dj = dd[j];
+  for (int64_t i = (int64_t)blockIdx.x * ET + threadIdx.x; i < n; i += (int64_t)gridDim.x * ET) {
+    const double v = (dd[i] * S[i + j * n]) * dj;
+    L[i + j * n] = (i == j ? 1.0 : 0.0) - v;
+  }
+}
+
+static void laplacian_spectrum(const double* d_S, int64_t n, std::vector<double>& vals) {
+  Context& c = ctx();
+  RS_REQUIRE(n <= 46340, "get_components: n too large for the dense eigensolver");
+  DevBuf<double> ones(n), deg(n), L((size_t)n * n), lam(n);
+  RS_LAUNCH(k_fill_ones, (unsigned)cdiv(n, ET), ET, 0, ones.p, n);
+  DenseMatvec mv;
+  mv.init(d_S, n, n);
+  mv.mul_n(ones.p, deg.p);                                   // degree = S 1      (R :98)
+  RS_LAUNCH(k_inv_sqrt, (unsigned)cdiv(n, ET), ET, 0, deg.p, n);
+  dim3 grid((unsigned)std::min<int64_t>(cdiv(n, ET), 64), (unsigned)std::min<int64_t>(n, 65535));
+  RS_REQUIRE(n <= 65535, "get_components: n too large for this launch shape");
+  RS_LAUNCH(k_laplacian, grid, ET, 0, d_S, deg.p, n, L.p);
+  int lwork = 0;
+  RS_CUSOLVER(cusolverDnDsyevd_bufferSize(c.cusolver, CUSOLVER_EIG_MODE_NOVECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, L.p,
+                                          (int)n, lam.p, &lwork));
+  DevBuf<double> work((size_t)lwork);
+  DevBuf<int> info(1);
+  {
+    Phase ph("eig");
+    RS_CUSOLVER(cusolverDnDsyevd(c.cusolver, CUSOLVER_EIG_MODE_NOVECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, L.p, (int)n,
+                                 lam.p, work.p, lwork, info.p));
+  }
+  vals.resize(n);
+  int hinfo = 0;
+  RS_CUDA(cudaMemcpyAsync(vals.data(), lam.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+  RS_CUDA(cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  RS_CUDA(cudaStreamSynchronize(c.stream));
+  RS_REQUIRE(hinfo == 0, "get_components: eigensolver failed");
+  for (auto& v : vals) v = std::fabs(v);                     // abs(Re(.))   (R :102)
+  std::sort(vals.begin(), vals.end());                       // sort         (R :104)
+}
+
+void get_components(const double* d_S, int64_t n, double tol, double* h_vals, int32_t* n_eigs) {
+  std::vector<double> vals;
+  laplacian_spectrum(d_S, n, vals);
+  int cnt = 0;
+  for (double v : vals) cnt += v <= tol;
+  if (h_vals) std::memcpy(h_vals, vals.data(), sizeof(double) * n);
+  if (n_eigs) *n_eigs = cnt;
+}
+
+// ---- a17: consensus ---------------------------------------------------------------------------
+// consen[i,j] = #{r : lab[r][i] == lab[r][j]}, zeroed when <= R*tau, (c + c^T)/2 == c.
+__global__ void k_consensus(const int32_t* __restrict__ lab, int R, int64_t n, double cut, double* __restrict__ C) {
+  extern __shared__ int32_t sl[];  // R x 32 (rows i) + R x 32 (cols j)
+  int32_t* li = sl;
+  int32_t* lj = sl + R * 32;
+  const int64_t i0 = (int64_t)blockIdx.x * 32, j0 = (int64_t)blockIdx.y * 32;
+  for (int e = threadIdx.y * 32 + threadIdx.x; e < R * 32; e += 32 * blockDim.y) {
+    const int r = e / 32, t = e % 32;
+    li[e] = i0 + t < n ? lab[(int64_t)r * n + i0 + t] : -1;
+    lj[e] = j0 + t < n ? lab[(int64_t)r * n + j0 + t] : -2;
+  }
+  __syncthreads();
+  const int64_t i = i0 + threadIdx.x;
+  for (int c = threadIdx.y; c < 32; c += blockDim.y) {
+    const int64_t j = j0 + c;
+    if (i >= n || j >= n) continue;
+    int cnt = 0;
+    for (int r = 0; r < R; ++r) cnt += li[r * 32 + threadIdx.x] == lj[r * 32 + c];
+    const double v = (double)cnt;
+    C[i + j * n] = v <= cut ? 0.0 : v;
+  }
+}
+void consensus_dense(const int32_t* d_labels, int R, int64_t n, double tau, double* d_consen) {
+  Phase ph("consensus");
+  dim3 grid((unsigned)cdiv(n, 32), (unsigned)cdiv(n, 32)), block(32, 8);
+  RS_REQUIRE(cdiv(n, 32) <= 65535, "consensus: n too large");
+  RS_LAUNCH(k_consensus, grid, block, sizeof(int32_t) * R * 64, d_labels, R, n, (double)R * tau, d_consen);
+}
+
+// ---- a16: PAM (k-medoids BUILD + SWAP, cluster::pam variant 'original') ------------------------
+__global__ void k_pairwise_dist(const double* __restrict__ P, int64_t n, int dim, double* __restrict__ D) {
+  const int64_t j = blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * ET + threadIdx.x; i < n; i += (int64_t)gridDim.x * ET) {
+    double acc = 0;
+    for (int c = 0; c < dim; ++c) {
+      const double diff = __dsub_rn(P[i + (int64_t)c * n], P[j + (int64_t)c * n]);
+      acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+    }
+    D[i + j * n] = sqrt(acc);
+  }
+}
+__global__ void k_max_partial(const double* __restrict__ a, int64_t count, double* __restrict__ partial) {
+  __shared__ double sm[ET / 32];
+  double mx = -INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * ET + threadIdx.x; i < count; i += (int64_t)gridDim.x * ET) mx = fmax(mx, a[i]);
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < ET / 32; ++w) mx = fmax(mx, sm[w]);
+    partial[blockIdx.x] = mx;
+  }
+}
+// BUILD gain of candidate i: sum_j max(dysma[j] - d(i,j), 0); medoids get -inf    (one CTA per i)
+__global__ void k_build_gain(const double* __restrict__ D, int64_t n, const double* __restrict__ dysma,
+                             const int* __restrict__ is_med, double* __restrict__ gain) {
+  __shared__ double sm[ET / 32 + 1];
+  const int64_t i = blockIdx.x;
+  const double* row = D + i * n;  // D symmetric: column i == row i
+  double acc = 0;
+  for (int64_t j = threadIdx.x; j < n; j += ET) {
+    const double cmd = dysma[j] - row[j];
+    if (cmd > 0) acc += cmd;
+  }
+  acc = block_sum<ET>(acc, sm);
+  if (threadIdx.x == 0) gain[i] = is_med[i] ? -INFINITY : acc;
+}
+__global__ void k_min_update(const double* __restrict__ D, int64_t n, int64_t med, double* __restrict__ dysma) {
+  const int64_t j = (int64_t)blockIdx.x * ET + threadIdx.x;
+  if (j < n) dysma[j] = fmin(dysma[j], D[j + med * n]);
+}
+// nearest / second-nearest medoid distance per object
+__global__ void k_nearest_two(const double* __restrict__ D, int64_t n, const int* __restrict__ med, int k, double s,
+                              double* __restrict__ dysma, double* __restrict__ dysmb) {
+  const int64_t j = (int64_t)blockIdx.x * ET + threadIdx.x;
+  if (j >= n) return;
+  double a = s, b = s;
+  for (int t = 0; t < k; ++t) {
+    const double d = D[j + (int64_t)med[t] * n];
+    if (a > d) { b = a; a = d; } else if (b > d) { b = d; }
+  }
+  dysma[j] = a;
+  dysmb[j] = b;
+}
+// SWAP cost T[h][t] = sum_j C_{j, med[t], h} for every non-medoid h (one CTA per h)   [KR p.104]
+static constexpr int PAM_KMAX = 64;
+__global__ void k_swap_cost(const double* __restrict__ D, int64_t n, const int* __restrict__ med, int k,
+                            const int* __restrict__ is_med, const double* __restrict__ dysma,
+                            const double* __restrict__ dysmb, double* __restrict__ T) {
+  __shared__ double sm[ET / 32 + 1];
+  const int64_t h = blockIdx.x;
+  if (is_med[h]) {
+    for (int t = threadIdx.x; t < k; t += ET) T[h * k + t] = INFINITY;
+    return;
+  }
+  const double* dh = D + h * n;
+  double shared_term = 0;  // contribution common to all medoids: objects not closest to i
+  // pass 1: common term
+  for (int64_t j = threadIdx.x; j < n; j += ET) {
+    const double a = dysma[j], d = dh[j];
+    if (d < a) shared_term += d - a;
+  }
+  shared_term = block_sum<ET>(shared_term, sm);
+  // pass 2: per-medoid correction over the objects whose closest-medoid distance equals d(i,j)
+  for (int t = 0; t < k; ++t) {
+    const double* di = D + (int64_t)med[t] * n;
+    double acc = 0;
+    for (int64_t j = threadIdx.x; j < n; j += ET) {
+      const double a = dysma[j];
+      if (di[j] == a) {
+        const double d = dh[j], b = dysmb[j];
+        const double small = b > d ? d : b;
+        acc += (small - a) - (d < a ? d - a : 0.0);
+      }
+    }
+    acc = block_sum<ET>(acc, sm);
+    if (threadIdx.x == 0) T[h * k + t] = shared_term + acc;
+  }
+}
+// lexicographic-first minimum of T over (h, t)
+__global__ void k_argmin_first(const double* __restrict__ T, int64_t count, double* __restrict__ out_val,
+                               long long* __restrict__ out_idx) {
+  __shared__ double sv[ET];
+  __shared__ long long si[ET];
+  double bv = INFINITY;
+  long long bi = -1;
+  for (int64_t e = threadIdx.x; e < count; e += ET) {
+    const double v = T[e];
+    if (v < bv) { bv = v; bi = e; }
+  }
+  sv[threadIdx.x] = bv; si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = ET / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const double v2 = sv[threadIdx.x + o];
+      const long long i2 = si[threadIdx.x + o];
+      if (i2 >= 0 && (v2 < sv[threadIdx.x] || (v2 == sv[threadIdx.x] && (si[threadIdx.x] < 0 || i2 < si[threadIdx.x])))) {
+        sv[threadIdx.x] = v2; si[threadIdx.x] = i2;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { *out_val = sv[0]; *out_idx = si[0]; }
+}
+// last index among the maxima of gain (pam.c: `ammax <= beter[i]`)
+__global__ void k_argmax_last(const double* __restrict__ g, int64_t count, long long* __restrict__ out_idx) {
+  __shared__ double sv[ET];
+  __shared__ long long si[ET];
+  double bv = -INFINITY;
+  long long bi = -1;
+  for (int64_t e = threadIdx.x; e < count; e += ET) {
+    const double v = g[e];
+    if (v >= bv && v > -INFINITY) { bv = v; bi = e; }
+  }
+  sv[threadIdx.x] = bv; si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = ET / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const double v2 = sv[threadIdx.x + o];
+      const long long i2 = si[threadIdx.x + o];
+      if (i2 >= 0 && (v2 > sv[threadIdx.x] || (v2 == sv[threadIdx.x] && i2 > si[threadIdx.x]))) {
+        sv[threadIdx.x] = v2; si[threadIdx.x] = i2;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out_idx = si[0];
+}
+__global__ void k_assign(const double* __restrict__ D, int64_t n, const int* __restrict__ med, int k,
+                         int32_t* __restrict__ near) {
+  const int64_t j = (int64_t)blockIdx.x * ET + threadIdx.x;
+  if (j >= n) return;
+  int best = 0;
+  double bd = D[j + (int64_t)med[0] * n];
+  for (int t = 1; t < k; ++t) {
+    const double d = D[j + (int64_t)med[t] * n];
+    if (d < bd) { bd = d; best = t; }
+  }
+  for (int t = 0; t < k; ++t)
+    if (med[t] == j) best = t;
+  near[j] = best;
+}
+
+struct PamEngine {
+  int64_t n = 0;
+  DevBuf<double> D, dysma, dysmb, gain, T, scal;
+  DevBuf<int> is_med, med;
+  DevBuf<long long> lidx;
+  DevBuf<int32_t> near;
+  double s = 0;
+  std::vector<int> build_order;  // greedy BUILD sequence (shared by every k)
+
+  void init(const double* d_P, int64_t n_, int dim, int kmax) {
+    n = n_;
+    cudaStream_t st = ctx().stream;
+    RS_REQUIRE(n <= 65535, "pam: more than 65535 observations (cluster::pam has the same limit)");
+    D.alloc((size_t)n * n); dysma.alloc(n); dysmb.alloc(n); gain.alloc(n); T.alloc((size_t)n * kmax); scal.alloc(256);
+    is_med.alloc(n); med.alloc(kmax); lidx.alloc(1); near.alloc(n);
+    dim3 grid((unsigned)std::min<int64_t>(cdiv(n, ET), 64), (unsigned)n);
+    RS_LAUNCH(k_pairwise_dist, grid, ET, 0, d_P, n, dim, D.p);
+    RS_LAUNCH(k_max_partial, 148, ET, 0, D.p, n * n, scal.p);
+    std::vector<double> part(148);
+    scal.download(part.data(), 148, st);
+    RS_CUDA(cudaStreamSynchronize(st));
+    double mx = 0;
+    for (double v : part) mx = std::max(mx, v);
+    s = 1.1 * mx + 1.0;
+    // BUILD once up to kmax; the medoid set for k is the first k picks
+    std::vector<double> init(n, s);
+    dysma.upload(init.data(), n, st);
+    is_med.zero(st);
+    build_order.clear();
+    const int one = 1;
+    for (int t = 0; t < kmax; ++t) {
+      RS_LAUNCH(k_build_gain, (unsigned)n, ET, 0, D.p, n, dysma.p, is_med.p, gain.p);
+      RS_LAUNCH(k_argmax_last, 1, ET, 0, gain.p, n, lidx.p);
+      long long pick = -1;
+      RS_CUDA(cudaMemcpyAsync(&pick, lidx.p, sizeof(long long), cudaMemcpyDeviceToHost, st));
+      RS_CUDA(cudaStreamSynchronize(st));
+      RS_REQUIRE(pick >= 0, "pam: BUILD found no candidate");
+      build_order.push_back((int)pick);
+      RS_CUDA(cudaMemcpyAsync(is_med.p + pick, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+      RS_LAUNCH(k_min_update, (unsigned)cdiv(n, ET), ET, 0, D.p, n, (int64_t)pick, dysma.p);
+    }
+    RS_CUDA(cudaStreamSynchronize(st));
+  }
+
+  // SWAP from the BUILD prefix of size k; returns sorted medoids and first-appearance labels
+  void solve(int k, std::vector<int>& medoids, std::vector<int32_t>& labels) {
+    cudaStream_t st = ctx().stream;
+    RS_REQUIRE(k >= 1 && k <= (int)build_order.size() && k <= PAM_KMAX, "pam: k out of range");
+    std::vector<int> flags(n, 0);
+    medoids.assign(build_order.begin(), build_order.begin() + k);
+    std::sort(medoids.begin(), medoids.end());
+    for (int m : medoids) flags[m] = 1;
+    is_med.upload(flags.data(), n, st);
+    med.upload(medoids.data(), k, st);
+    RS_LAUNCH(k_nearest_two, (unsigned)cdiv(n, ET), ET, 0, D.p, n, med.p, k, s, dysma.p, dysmb.p);
+    double sky = 0;
+    {  // sky = sum dysma
+      std::vector<double> h(n);
+      dysma.download(h.data(), n, st);
+      RS_CUDA(cudaStreamSynchronize(st));
+      for (double v : h) sky += v;
+    }
+    for (int guard = 0; guard < 100000 && k < n; ++guard) {
+      RS_LAUNCH(k_swap_cost, (unsigned)n, ET, 0, D.p, n, med.p, k, is_med.p, dysma.p, dysmb.p, T.p);
+      RS_LAUNCH(k_argmin_first, 1, ET, 0, T.p, n * k, scal.p, lidx.p);
+      double dz = 0;
+      long long where = -1;
+      RS_CUDA(cudaMemcpyAsync(&dz, scal.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+      RS_CUDA(cudaMemcpyAsync(&where, lidx.p, sizeof(long long), cudaMemcpyDeviceToHost, st));
+      RS_CUDA(cudaStreamSynchronize(st));
+      if (!(where >= 0) || !(dz < -16.0 * 2.220446049250313e-16 * std::fabs(sky))) break;
+      const int hbest = (int)(where / k), tbest = (int)(where % k);
+      flags[medoids[tbest]] = 0;
+      flags[hbest] = 1;
+      medoids[tbest] = hbest;
+      std::sort(medoids.begin(), medoids.end());
+      sky += dz;
+      is_med.upload(flags.data(), n, st);
+      med.upload(medoids.data(), k, st);
+      RS_LAUNCH(k_nearest_two, (unsigned)cdiv(n, ET), ET, 0, D.p, n, med.p, k, s, dysma.p, dysmb.p);
+    }
+    RS_LAUNCH(k_assign, (unsigned)cdiv(n, ET), ET, 0, D.p, n, med.p, k, near.p);
+    std::vector<int32_t> nr(n);
+    near.download(nr.data(), n, st);
+    RS_CUDA(cudaStreamSynchronize(st));
+    labels.assign(n, 0);
+    std::vector<int> seen(k, 0);
+    int nxt = 0;
+    for (int64_t j = 0; j < n; ++j) {
+      if (!seen[nr[j]]) seen[nr[j]] = ++nxt;
+      labels[j] = seen[nr[j]];
+    }
+  }
+};
+
+void pam(const double* d_P, int64_t n, int dim, int k, int32_t* h_labels, int32_t* h_medoids) {
+  Phase ph("pam");
+  RS_REQUIRE(k >= 1 && k < n, "pam: need 1 <= k < n");
+  PamEngine eng;
+  eng.init(d_P, n, dim, k);
+  std::vector<int> med;
+  std::vector<int32_t> lab;
+  eng.solve(k, med, lab);
+  if (h_labels) std::memcpy(h_labels, lab.data(), sizeof(int32_t) * n);
+  if (h_medoids) for (int t = 0; t < k; ++t) h_medoids[t] = med[t];
+}
+
+// ---- CountClusters ------------------------------------------------------------------------------
+void count_clusters(const double* d_S, int64_t n, double tol, int lo, int hi, int n_comp, int32_t* upper,
+                    int32_t* lower, double* h_vals, int32_t* n_eigs) {
+  cudaStream_t st = ctx().stream;
+  RS_REQUIRE(lo >= 1 && hi >= lo && hi < n, "count_clusters: invalid range");
+  RS_REQUIRE(n_comp >= 1 && n_comp <= n, "count_clusters: invalid n_comp");
+  std::vector<double> vals;
+  laplacian_spectrum(d_S, n, vals);                                       // R :63
+  int solo = 0;
+  for (double v : vals) solo += v <= tol;
+  const double tau = solo <= 5 ? 0.3 : (solo <= 10 ? 0.4 : 0.5);          // R :64-70
+  // GetEnsemble (R :125-154): PCA scores of t(S), PAM for every k in range, consensus
+  DevBuf<double> scores((size_t)n * n_comp);
+  std::vector<double> eig;
+  pca_spectrum(d_S, n, n, eig, scores.p, n_comp);                         // R :133
+  const int R = hi - lo + 1;
+  std::vector<int32_t> table((size_t)R * n);
+  {
+    Phase ph("pam");
+    PamEngine eng;
+    eng.init(scores.p, n, n_comp, hi);
+    std::vector<int> med;
+    std::vector<int32_t> lab;
+    for (int k = lo; k <= hi; ++k) {                                      // R :136-138
+      eng.solve(k, med, lab);
+      std::copy(lab.begin(), lab.end(), table.begin() + (size_t)(k - lo) * n);
+    }
+  }
+  DevBuf<int32_t> d_table(table.size());
+  d_table.upload(table.data(), table.size(), st);
+  DevBuf<double> consen((size_t)n * n);
+  consensus_dense(d_table.p, R, n, tau, consen.p);                        // R :143-153
+  laplacian_spectrum(consen.p, n, vals);                                  // R :72
+  double best = -INFINITY;
+  int arg = 0;
+  for (int64_t i = 0; i + 1 < n; ++i) {                                   // R :74-75 (first maximum)
+    const double g = vals[i + 1] - vals[i];
+    if (g > best) { best = g; arg = (int)i + 1; }
+  }
+  int low = 0;
+  for (double v : vals) low += v <= tol;                                  // R :78
+  if (upper) *upper = arg;
+  if (lower) *lower = low;
+  if (h_vals) std::memcpy(h_vals, vals.data(), sizeof(double) * n);
+  if (n_eigs) *n_eigs = low;
+}
+
+}  // namespace rs

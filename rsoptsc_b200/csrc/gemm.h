@@ -1,0 +1,17 @@
+// Dense FP64(-equivalent) contractions of the path (gemm.cu).  All operands column-major,
+// leading dimension == row count.
+#pragma once
+#include "common.h"
+
+namespace rs {
+// G (cols x cols, lower triangle valid) = A^T A,  A: rows x cols
+void gram_AtA(const double* A, int64_t rows, int64_t cols, double* G);
+// G (rows x rows, lower triangle valid) = A A^T
+void gram_AAt(const double* A, int64_t rows, int64_t cols, double* G);
+// C (M x N) = A (M x K) * B (K x N)
+void gemm_nn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
+// C (M x N) = A (M x K) * B^T, B: N x K
+void gemm_nt(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
+// C (M x N) = A^T * B, A: K x M, B: K x N
+void gemm_tn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
+}  // namespace rs

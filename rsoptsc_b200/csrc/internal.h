@@ -1,0 +1,117 @@
+// Internal interfaces between the translation units of librsoptsc_b200.so.
+#pragma once
+#include <atomic>
+#include <map>
+
+#include "common.h"
+
+namespace rs {
+
+// ---- launch accounting + phase timers (capi.cu) ------------------------------------
+extern std::atomic<int64_t> g_launches;
+struct Phase {  // RAII: device time of a region on the library stream
+  int id;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  explicit Phase(const char* name);
+  ~Phase();
+};
+
+#define RS_LAUNCH(kernel, grid, block, smem, ...)                                   \
+  do {                                                                              \
+    kernel<<<(grid), (block), (smem), ::rs::ctx().stream>>>(__VA_ARGS__);           \
+    ::rs::g_launches.fetch_add(1, std::memory_order_relaxed);                       \
+    RS_KERNEL_CHECK();                                                              \
+  } while (0)
+
+// ---- support of Z: CSR over rows (the reference's mask is per row jj, SimilarityM.R:90-92)
+// plus the CSC view the column-local ADMM kernels walk. ------------------------------
+struct Support {
+  int64_t n = 0, nnz = 0;
+  DevBuf<int> rowptr, col, rowof;      // CSR (row-major position p); rowof[p] = row of entry p
+  DevBuf<int> colptr, rowidx, csrpos;  // CSC: for column j, entries q in [colptr[j], colptr[j+1])
+                                       //      rowidx[q] = i, csrpos[q] = p
+  std::vector<int> h_rowptr, h_col;
+  int max_col_nnz = 0;
+};
+void build_support_from_idx(Support& s, const int32_t* h_idx, int64_t n, int K);
+void build_support_from_dense_mask(Support& s, const double* h_D, int64_t n);
+
+// ---- dense elementwise (dense.cu) ---------------------------------------------------
+void normalize_columns(const double* d_data, int64_t m, int64_t n, double* d_X);
+// A = -Y3/mu (+ Z scattered on the support); returns ||A||_F^2
+double build_A(const Support& s, const double* d_Zs, const double* d_Y3, double mu, double* d_A);
+// q[p] = Zs[p] - J[i,j] + Y3[i,j]/mu on the support (J may be null == 0)
+void gather_support_term(const Support& s, const double* d_Zs, const double* d_J, const double* d_Y3,
+                         double mu, double* d_q);
+// Y3 += mu*(Z - J) ; returns ||Z - J||_F^2   (J may be null == 0)
+double update_Y3(const Support& s, const double* d_Zs, const double* d_J, double mu, double* d_Y3);
+void scale_columns(double* d_T, int64_t rows, int64_t cols, const double* d_scale);
+void threshold_symmetrise_dense(const double* d_Z, int64_t n, double* d_W);
+void threshold_symmetrise_sparse(const Support& s, const double* d_Zs, double* d_W /* n x n, zeroed here */);
+void scatter_support_dense(const Support& s, const double* d_Zs, double* d_Z /* n x n, zeroed here */);
+double frob2(const double* d_a, int64_t count);
+
+// ---- column-local ADMM step (admm_kernels.cu) ---------------------------------------
+struct AdmmState {
+  int64_t m = 0, n = 0;
+  const double* X = nullptr;  // m x n normalised
+  DevBuf<double> Zs;          // nnz, CSR order
+  DevBuf<double> XXZ, E, Y1, R, M;  // m x n
+  DevBuf<double> Y2;          // n
+  DevBuf<double> q;           // nnz support term
+  DevBuf<double> colacc;      // n  per-column ||XXZ||^2
+};
+void admm_E_update(AdmmState& st, double lambda, double mu);
+void admm_Z_update(AdmmState& st, const Support& s, double mu, double eta);
+// XXZ = X - X Z ; Y1 += mu (XXZ - E) ; M = XXZ - E ; returns ||XXZ||_F^2
+double admm_residual_update(AdmmState& st, const Support& s, double mu, bool update_duals);
+
+// ---- spectral norm (lanczos.cu) -----------------------------------------------------
+// Largest singular value of the column-major rows x cols matrix (Lanczos on the smaller Gram
+// operator, full reorthogonalisation).  rel_tol on the Ritz value.
+double spectral_norm(const double* d_M, int64_t rows, int64_t cols, double rel_tol = 1e-13);
+// Host: eigen-decomposition of a symmetric tridiagonal (d: k diag, e: k-1 off-diag).
+// On return d holds ascending eigenvalues, Zv (k x k column-major, may be null) eigenvectors.
+void tridiag_eig(std::vector<double>& d, std::vector<double>& e, std::vector<double>* Zv);
+
+// ---- singular value thresholding (svt.cu) -------------------------------------------
+struct SvtWorkspace {
+  int64_t n = 0;
+  DevBuf<double> G, T, lam, work;
+  DevBuf<int> info;
+  int lwork = 0;
+  void ensure(int64_t n);
+};
+// J = SVT_tau(A) written over A.  Returns rank(J).
+int64_t svt_inplace(SvtWorkspace& ws, double* d_A, int64_t n, double tau);
+
+// ---- drivers --------------------------------------------------------------------------
+struct AdmmResult {
+  double E = 0;
+  int iters = 0, stop = 0, n_svt = 0;
+  double err1[100], err2[100];
+};
+// Runs computeM on device-resident X with the given support; Zs (nnz) returned in st.Zs.
+void run_admm(const double* d_X, int64_t m, int64_t n, const Support& s, double lambda,
+              AdmmState& st, AdmmResult& res);
+
+// knn.cu
+void knn_bruteforce(const double* d_emb, int64_t n, int64_t ld, int dim, int K, int32_t* d_idx);
+// pca.cu : eig (host, min(m,n) descending), optional device emb n x ncomp
+void pca_spectrum(const double* d_X, int64_t m, int64_t n, std::vector<double>& eig, double* d_emb,
+                  int ncomp);
+int choose_K(const std::vector<double>& eig);
+
+// nmf.cu
+struct NmfResult { int iters = 0; };
+void nmf_lee(const double* d_V, int64_t n, int k, int max_iter, double* h_basis, double* h_coef,
+             int32_t* h_labels, NmfResult& res);
+
+// eigengap.cu
+void get_components(const double* d_S, int64_t n, double tol, double* h_vals, int32_t* n_eigs);
+void consensus_dense(const int32_t* d_labels, int R, int64_t n, double tau, double* d_consen);
+void pam(const double* d_P, int64_t n, int dim, int k, int32_t* h_labels, int32_t* h_medoids);
+void count_clusters(const double* d_S, int64_t n, double tol, int lo, int hi, int n_comp,
+                    int32_t* upper, int32_t* lower, double* h_vals, int32_t* n_eigs);
+
+}  // namespace rs

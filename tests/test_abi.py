@@ -1,0 +1,78 @@
+"""The C-ABI library loads and exports every symbol include/rsoptsc_b200.h declares; without
+a GPU the compute entry points fail loudly (no CPU fallback).  CPU only."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from rsoptsc_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "rsoptsc_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rsoptsc_[a-zA-Z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(lib):
+    names = _declared()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(lib, name), "missing export " + name
+    assert sorted(_lib.SIGNATURES) == names, "ctypes table out of sync with the header"
+    assert lib.rsoptsc_abi_version() == 1
+
+
+def test_no_reference_to_oracle_in_product():
+    # the product path must never import the oracle
+    pkg = os.path.join(ROOT, "rsoptsc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".c")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def _has_gpu(lib):
+    return lib.rsoptsc_init(-1) == 0
+
+
+def test_fails_loudly_without_gpu(lib):
+    if _has_gpu(lib):
+        pytest.skip("GPU present")
+    x = np.ones((4, 4), order="F")
+    out = np.empty_like(x)
+    st = lib.rsoptsc_normalize(x.ctypes.data_as(_lib.c_double_p), 4, 4, out.ctypes.data_as(_lib.c_double_p))
+    assert st != 0
+    assert b"no CPU fallback" in lib.rsoptsc_last_error()
+    from rsoptsc_b200 import api
+    with pytest.raises(_lib.RsoptscError):
+        api.normalize(x)
+
+
+def test_host_tridiag_eig(lib):
+    rng = np.random.default_rng(0)
+    for k in (1, 2, 7, 64, 300):
+        d = rng.normal(size=k)
+        e = rng.normal(size=max(k - 1, 1))
+        T = np.diag(d) + (np.diag(e[:k - 1], 1) + np.diag(e[:k - 1], -1) if k > 1 else 0)
+        dd = d.copy()
+        V = np.zeros((k, k), order="F")
+        st = lib.rsoptsc_host_tridiag_eig(k, dd.ctypes.data_as(_lib.c_double_p), e.ctypes.data_as(_lib.c_double_p),
+                                          V.ctypes.data_as(_lib.c_double_p))
+        assert st == 0
+        assert np.allclose(dd, np.linalg.eigvalsh(T), atol=1e-12 * max(1, k))
+        assert np.abs(T @ V - V * dd).max() < 1e-12 * max(1, k)
+
+
+def test_host_choose_K_matches_oracle(lib):
+    from oracle import rsoptsc_oracle as O
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        L = int(rng.integers(5, 400))
+        eig = np.sort(rng.gamma(0.5, size=L))[::-1].copy()
+        assert lib.rsoptsc_host_choose_K(eig.ctypes.data_as(_lib.c_double_p), L) == O.choose_K(eig)

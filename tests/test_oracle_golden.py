@@ -1,0 +1,59 @@
+"""Pin the CPU oracle against the reference's own known answers.
+CPU only; the slowest case (computeM on the 24,470 x 720 Joost matrix) takes ~45 s."""
+import numpy as np
+
+from oracle import rsoptsc_oracle as O
+
+
+def test_get_components_known_answer(joost):
+    # tests/testthat/testClusterNumber.R:4-7
+    r = O.GetComponents(joost["S"], tol=0.01)
+    assert r["n_eigs"] == 6
+    assert np.all(np.diff(r["val"]) >= 0)
+
+
+def test_nmf_reproduces_fixture_basis_and_labels(joost):
+    # stored pair joostTest$S -> joostTest$H / $labels (R/sysdata.rda)
+    r = O.nmf_lee(joost["S"], 9)
+    assert r["iters"] == 510
+    rel = np.linalg.norm(r["W"] - joost["H"]) / np.linalg.norm(joost["H"])
+    assert rel < 1e-12
+    assert np.array_equal(O.labels_from_basis(r["W"]), joost["labels"])
+    assert np.allclose(r["W"].sum(axis=0), 1.0, atol=1e-12)
+
+
+def test_count_clusters_matches_fixture_rank(joost):
+    # rank of joostTest$H is 9; CountClusters(S) must give the same upper bound
+    r = O.CountClusters(joost["S"], n_comp=3)
+    assert r["upper_bound"] == 9 and r["solo_count"] == 6 and r["tau"] == 0.4
+
+
+def test_computeM_known_answer(joost):
+    # tests/testthat/testL2R2.R:4-15  E = 16.7979 +- 1e-5
+    X = O.normalize_columns(joost["data"].toarray())
+    forb = O.mask_from_idx(joost["idx"], joost["n"])
+    trace = []
+    r = O.computeM(forb, X, 0.5, literal=False, trace=trace)
+    assert abs(r["E"] - 16.7979) <= 1e-5
+    assert r["iters"] == 27 and r["stop"] == "error min"
+    # SURVEY.md appendix B trace
+    assert abs(trace[8][3] - 0.38807218) < 1e-7 and trace[9][2] == 59
+    Z = r["Z"]
+    assert np.count_nonzero(Z) == 7200 and Z.min() >= 0
+    W = O.threshold_symmetrise(Z)
+    assert np.count_nonzero(W) == 8622 and abs(W.sum() - 449.352) < 1e-3
+
+
+def test_knn_self_included_and_mask():
+    rng = np.random.default_rng(1)
+    emb = rng.normal(size=(200, 3))
+    idx = O.knn_indices(emb, 10)
+    assert np.array_equal(idx[:, 0], np.arange(200))          # self is the nearest (distance 0)
+    forb = O.mask_from_idx(idx, 200)
+    assert np.all((~forb).sum(axis=1) == 10) and not forb.diagonal().any()
+
+
+def test_choose_K_bounds():
+    assert O.choose_K(np.array([5.0, 1.0] + [1e-3] * 50)) == 10
+    flat = np.ones(400)
+    assert O.choose_K(flat) == 30
