@@ -46,6 +46,12 @@ double rsoptsc_phase_ms(const char* name);
 int64_t rsoptsc_phase_calls(const char* name);
 int rsoptsc_timers_reset(void);
 int rsoptsc_timers_enable(int on);
+/* Caller-defined device timer (CUDA events on the library stream) accumulated under `name`;
+ * read back with rsoptsc_phase_ms(name).  bench.py brackets every timed step with these. */
+/* i-th phase name seen so far, NULL past the end (enumeration for reports). */
+const char* rsoptsc_phase_name(int32_t i);
+int rsoptsc_timer_begin(const char* name);
+int rsoptsc_timer_end(const char* name);
 
 /* device-memory helpers for the *_dev entry points */
 int rsoptsc_dev_alloc(void** dptr, int64_t bytes);

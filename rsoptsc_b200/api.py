@@ -101,16 +101,21 @@ def threshold_symmetrise(Z):
     return W
 
 
-def SimilarityM(lam=0.5, data=None, embedding=None, K=None, dense=True, sparse=False):
+def SimilarityM(lam=0.5, data=None, embedding=None, K=None, dense=True, sparse=False, W_out=None):
     """SimilarityM(lambda, data, ...) of R/SimilarityM.R:27 -> dict(W, E, nl_embedding, ...).
 
     `embedding` is what Rtsne/umap produce in the reference (n x >= 3); None selects the
-    deterministic in-library PCA embedding.  `K` forces the neighbour count (config 5)."""
+    deterministic in-library PCA embedding.  `K` forces the neighbour count (config 5).
+    `W_out` (optional, n x n float64 Fortran-ordered, e.g. pinned memory) receives W."""
     lib = _lib.init()
     d = _f64(data)
     m, n = d.shape
     emb = None if embedding is None else _f64(embedding)
-    W = np.empty((n, n), dtype=np.float64, order="F") if dense else None
+    if W_out is not None:
+        if W_out.shape != (n, n) or W_out.dtype != np.float64 or not W_out.flags.f_contiguous:
+            raise ValueError("W_out must be an n x n float64 Fortran-ordered array")
+        dense = True
+    W = W_out if W_out is not None else (np.empty((n, n), dtype=np.float64, order="F") if dense else None)
     E, iters, Kout = C.c_double(0), C.c_int32(0), C.c_int32(0)
     emb_out = np.zeros((n, 3), dtype=np.float64, order="F")
     cap = C.c_int64(2 * n * 32 if sparse else 0)
@@ -202,6 +207,72 @@ def ClusterCells(similarityMatrix=None, n_clusters=None, n_comp=3, max_iter=2000
     return dict(H=r["W"], labels=r["labels"], ensemble=ensemble, iters=r["iters"], coef=r["H"])
 
 
+class DeviceBuffer:
+    """Library-owned device allocation (for the *_dev entry points: inputs resident in HBM)."""
+
+    def __init__(self, nbytes):
+        lib = _lib.init()
+        self.ptr = C.c_void_p(0)
+        self.nbytes = int(nbytes)
+        _lib.check(lib.rsoptsc_dev_alloc(C.byref(self.ptr), self.nbytes))
+
+    @classmethod
+    def from_host(cls, arr):
+        a = _f64(arr)
+        buf = cls(a.nbytes)
+        _lib.check(_lib.load().rsoptsc_dev_upload(buf.ptr, a.ctypes.data_as(C.c_void_p), a.nbytes))
+        return buf
+
+    def to_host(self, shape, dtype=np.float64):
+        out = np.empty(shape, dtype=dtype, order="F")
+        _lib.check(_lib.load().rsoptsc_dev_download(out.ctypes.data_as(C.c_void_p), self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            _lib.load().rsoptsc_dev_free(self.ptr)
+            self.ptr = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def SimilarityM_dev(lam, d_data, m, n, d_W=None, d_emb=None, emb_dim=0, K=None):
+    """Device-resident SimilarityM: d_data (m x n) and d_W (n x n) are DeviceBuffers."""
+    lib = _lib.init()
+    E, iters, Kout = C.c_double(0), C.c_int32(0), C.c_int32(0)
+    _lib.check(lib.rsoptsc_similarity_dev(d_data.ptr, m, n, d_emb.ptr if d_emb is not None else None, emb_dim,
+                                          float(lam), int(K or 0), d_W.ptr if d_W is not None else None,
+                                          C.byref(E), C.byref(iters), C.byref(Kout)))
+    return dict(E=float(E.value), iters=int(iters.value), K=int(Kout.value))
+
+
+def nmf_lee_dev(d_V, n, rank, max_iter=2000, want_factors=False):
+    """Device-resident NMF: d_V is a DeviceBuffer holding the n x n similarity."""
+    lib = _lib.init()
+    labels = np.empty(n, dtype=np.int32)
+    iters = C.c_int32(0)
+    basis = np.empty((n, rank), dtype=np.float64, order="F") if want_factors else None
+    _lib.check(lib.rsoptsc_nmf_lee_dev(d_V.ptr, n, int(rank), int(max_iter), _dp(basis) if want_factors else None,
+                                       None, _ip(labels), C.byref(iters)))
+    return dict(labels=labels, iters=int(iters.value), W=basis)
+
+
+def timer_begin(name):
+    _lib.check(_lib.load().rsoptsc_timer_begin(name.encode()))
+
+
+def timer_end(name):
+    _lib.check(_lib.load().rsoptsc_timer_end(name.encode()))
+
+
+def phase_ms(name):
+    return float(_lib.load().rsoptsc_phase_ms(name.encode()))
+
+
 def kernel_launches():
     return int(_lib.load().rsoptsc_kernel_launches())
 
@@ -211,15 +282,18 @@ def timers(enable=True):
     _lib.load().rsoptsc_timers_reset()
 
 
-PHASES = ["normalize", "pca", "knn", "dense_ew", "gram", "eig", "recon", "column_step", "lanczos", "symm", "nndsvd",
-          "nmf", "pam", "consensus"]
-
-
 def phase_report():
+    """{phase: {ms, calls}} for every library phase timed since the last timers() reset."""
     lib = _lib.load()
     out = {}
-    for p in PHASES:
-        ms = lib.rsoptsc_phase_ms(p.encode())
-        if ms >= 0:
-            out[p] = dict(ms=ms, calls=int(lib.rsoptsc_phase_calls(p.encode())))
+    i = 0
+    while True:
+        name = lib.rsoptsc_phase_name(i)
+        if name is None:
+            break
+        i += 1
+        ms = lib.rsoptsc_phase_ms(name)
+        calls = int(lib.rsoptsc_phase_calls(name))
+        if calls > 0:
+            out[name.decode()] = dict(ms=ms, calls=calls)
     return out

@@ -35,7 +35,7 @@ __global__ void k_E_update(const double* __restrict__ XXZ, const double* __restr
 }
 
 void admm_E_update(AdmmState& st, double lambda, double mu) {
-  Phase ph("column_step");
+  Phase ph("E_update");
   RS_LAUNCH(k_E_update, (unsigned)st.n, CT, 0, st.XXZ.p, st.Y1.p, st.m, lambda, mu, st.E.p, st.R.p);
 }
 
@@ -74,7 +74,7 @@ __global__ void k_Z_update(const double* __restrict__ X, const double* __restric
 }
 
 void admm_Z_update(AdmmState& st, const Support& s, double mu, double eta) {
-  Phase ph("column_step");
+  Phase ph("Z_update");
   RS_LAUNCH(k_Z_update, (unsigned)st.n, CT, 0, st.X, st.R.p, st.m, s.colptr.p, s.rowidx.p, s.csrpos.p, st.q.p, mu,
             eta, st.Zs.p, st.Y2.p);
 }
@@ -130,7 +130,7 @@ __global__ void k_sum_vec(const double* __restrict__ v, int64_t n, double* __res
 }
 
 double admm_residual_update(AdmmState& st, const Support& s, double mu, bool update_duals) {
-  Phase ph("column_step");
+  Phase ph("residual");
   RS_LAUNCH(k_residual, (unsigned)st.n, CT, 0, st.X, st.m, s.colptr.p, s.rowidx.p, s.csrpos.p, st.Zs.p, st.E.p, mu,
             update_duals ? 1 : 0, st.XXZ.p, st.Y1.p, st.M.p, st.colacc.p);
   RS_LAUNCH(k_sum_vec, 1, CT, 0, st.colacc.p, st.n, st.colacc.p + st.n);

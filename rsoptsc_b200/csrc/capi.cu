@@ -59,20 +59,18 @@ static int phase_id(const char* name) {
   return (int)g_phase_names.size() - 1;
 }
 Phase::Phase(const char* name) : id(-1) {
-  // nested phases are attributed to the outermost one only
-  if (!g_timers_on || !g_ctx.initialized || g_phase_depth++ > 0) return;
+  if (!g_timers_on || !g_ctx.initialized) return;
   id = phase_id(name);
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, g_ctx.stream);
 }
 Phase::~Phase() {
-  if (!g_timers_on || !g_ctx.initialized) return;
-  --g_phase_depth;
-  if (id < 0) return;
+  if (id < 0 || !g_ctx.initialized) return;
   cudaEventRecord(e1, g_ctx.stream);
   g_phases[id].pending.emplace_back(e0, e1);
   g_phases[id].calls++;
 }
+static std::unordered_map<std::string, cudaEvent_t> g_open_timers;
 static void resolve_phases() {
   if (!g_ctx.initialized) return;
   cudaStreamSynchronize(g_ctx.stream);
@@ -135,6 +133,30 @@ double rsoptsc_phase_ms(const char* name) {
   for (size_t i = 0; i < g_phase_names.size(); ++i)
     if (g_phase_names[i] == name) return g_phases[i].ms;
   return -1.0;
+}
+const char* rsoptsc_phase_name(int32_t i) {
+  return (i >= 0 && (size_t)i < g_phase_names.size()) ? g_phase_names[i].c_str() : nullptr;
+}
+int rsoptsc_timer_begin(const char* name) {
+  return guarded([&] {
+    cudaEvent_t e;
+    RS_CUDA(cudaEventCreate(&e));
+    RS_CUDA(cudaEventRecord(e, ctx().stream));
+    g_open_timers[name] = e;
+  });
+}
+int rsoptsc_timer_end(const char* name) {
+  return guarded([&] {
+    auto it = g_open_timers.find(name);
+    RS_REQUIRE(it != g_open_timers.end(), "timer_end without timer_begin");
+    cudaEvent_t e1;
+    RS_CUDA(cudaEventCreate(&e1));
+    RS_CUDA(cudaEventRecord(e1, ctx().stream));
+    const int id = phase_id(name);
+    g_phases[id].pending.emplace_back(it->second, e1);
+    g_phases[id].calls++;
+    g_open_timers.erase(it);
+  });
 }
 int64_t rsoptsc_phase_calls(const char* name) {
   for (size_t i = 0; i < g_phase_names.size(); ++i)

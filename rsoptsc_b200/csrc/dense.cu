@@ -131,7 +131,7 @@ __global__ void k_scatter_add(const int* __restrict__ rowof, const int* __restri
 }
 
 double build_A(const Support& s, const double* d_Zs, const double* d_Y3, double mu, double* d_A) {
-  Phase ph("dense_ew");
+  Phase ph("build_A");
   const int64_t nn = s.n * s.n;
   RS_LAUNCH(k_scale_neg, RED_BLOCKS * 2, 256, 0, d_Y3, mu, nn, d_A);
   if (s.nnz) RS_LAUNCH(k_scatter_add, cdiv(s.nnz, 256), 256, 0, s.rowof.p, s.col.p, d_Zs, s.nnz, s.n, 1.0, d_A);
@@ -151,7 +151,7 @@ __global__ void k_gather_term(const int* __restrict__ rowof, const int* __restri
 }
 void gather_support_term(const Support& s, const double* d_Zs, const double* d_J, const double* d_Y3, double mu,
                          double* d_q) {
-  Phase ph("dense_ew");
+  Phase ph("gather");
   if (s.nnz)
     RS_LAUNCH(k_gather_term, cdiv(s.nnz, 256), 256, 0, s.rowof.p, s.col.p, d_Zs, d_J, d_Y3, mu, s.nnz, s.n, d_q);
 }
@@ -197,7 +197,7 @@ __global__ void k_y3_add_Z(const int* __restrict__ rowof, const int* __restrict_
 }
 
 double update_Y3(const Support& s, const double* d_Zs, const double* d_J, double mu, double* d_Y3) {
-  Phase ph("dense_ew");
+  Phase ph("update_Y3");
   const int64_t nn = s.n * s.n;
   double total = 0;
   // order matters: the sparse kernel reads J on the support, so it may run after the dense one
