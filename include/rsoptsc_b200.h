@@ -140,6 +140,19 @@ int rsoptsc_count_clusters(const double* S, int64_t n, double tol, int32_t range
                            int32_t range_hi, int32_t n_comp, int32_t* upper_bound,
                            int32_t* lower_bound, double* vals, int32_t* n_eigs);
 
+/* ---- dense contraction backends (a4 Gram / reconstruction GEMMs) --------------------- */
+/* backend: 0 = cuBLAS FP64 (library baseline), 1 = tcgen05 split-integer (Ozaki) GEMM. */
+int rsoptsc_set_gemm_backend(int32_t backend);
+int32_t rsoptsc_get_gemm_backend(void);
+/* One contraction on host buffers (column-major), for parity tests and kernel benchmarks:
+ *   op 0: C (M x M, lower triangle valid) = A^T A,  A: K x M
+ *   op 1: C (M x N) = A B,    A: M x K, B: K x N
+ *   op 2: C (M x N) = A B^T,  A: M x K, B: N x K
+ *   op 3: C (M x N) = A^T B,  A: K x M, B: K x N
+ * reps >= 1 repetitions are timed with CUDA events; *ms_out (may be NULL) = mean ms per call. */
+int rsoptsc_debug_gemm(int32_t op, const double* A, const double* B, double* C, int64_t M,
+                       int64_t N, int64_t K, int32_t backend, int32_t reps, double* ms_out);
+
 /* ---- host-only helpers (no GPU needed; exercised by the CPU test-suite) ---------------- */
 /* Eigen-decomposition of a symmetric tridiagonal matrix (the small problem of every Lanczos
  * run): d (k) diagonal in / ascending eigenvalues out, e (k-1) off-diagonal, V (k x k

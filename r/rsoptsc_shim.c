@@ -1,0 +1,158 @@
+/* .Call shim between RSoptSC's R functions and librsoptsc_b200.so (include/rsoptsc_b200.h).
+ *
+ * Place in RSoptSC/src/ next to a Makevars with
+ *     PKG_CPPFLAGS = -I<repo>/include
+ *     PKG_LIBS     = -L<repo>/rsoptsc_b200 -lrsoptsc_b200 -Wl,-rpath,<repo>/rsoptsc_b200
+ * and add `useDynLib(RSoptSC, .registration = TRUE)` to NAMESPACE.
+ *
+ * R's C API is single-threaded: every entry point runs on R's main thread.  Errors are raised
+ * with Rf_error() only after the library call has returned (the library never longjmps and
+ * frees its own device memory before returning).  R is not installed in the build image, so
+ * this file is compile-checked against r/stub/Rinternals.h only; it has not been run under R.
+ */
+#ifdef RSOPTSC_STUB_R
+#include "stub/Rinternals.h"
+#else
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#endif
+#include <stdint.h>
+#include <string.h>
+
+#include "rsoptsc_b200.h"
+
+static void check(int status) {
+  if (status != 0) Rf_error("rsoptsc_b200: %s", rsoptsc_last_error());
+}
+
+static void dims(SEXP x, int64_t* nr, int64_t* nc) {
+  SEXP d = Rf_getAttrib(x, R_DimSymbol);
+  if (Rf_isNull(d)) Rf_error("matrix expected");
+  *nr = INTEGER(d)[0];
+  *nc = INTEGER(d)[1];
+}
+
+static SEXP named_list(int n, const char** names) {
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, n));
+  SEXP nm = PROTECT(Rf_allocVector(STRSXP, n));
+  for (int i = 0; i < n; ++i) SET_STRING_ELT(nm, i, Rf_mkChar(names[i]));
+  Rf_setAttrib(out, R_NamesSymbol, nm);
+  UNPROTECT(2);
+  return out;
+}
+
+/* .Call("rsoptsc_R_similarity", lambda, data, embedding_or_NULL, K_or_0)
+ * replaces the arithmetic of SimilarityM (R/SimilarityM.R:34-95); Rtsne/umap stay in R and
+ * hand their layout in as `embedding`.  Returns list(W, E, iters, K). */
+SEXP rsoptsc_R_similarity(SEXP lambda, SEXP data, SEXP emb, SEXP K) {
+  int64_t m, n, en = 0, ed = 0;
+  if (!Rf_isReal(data)) Rf_error("data must be a double matrix (use as.matrix)");
+  dims(data, &m, &n);
+  if ((double)n * (double)n > 2147483647.0 * 4096.0) Rf_error("n too large for a dense W; use the sparse interface");
+  const double* e = NULL;
+  if (!Rf_isNull(emb)) { dims(emb, &en, &ed); if (en != n) Rf_error("embedding must have one row per cell"); e = REAL(emb); }
+  SEXP W = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)n));   /* R_xlen_t sized internally */
+  double E = 0; int32_t iters = 0, Kout = 0;
+  int st = rsoptsc_similarity(REAL(data), m, n, e, (int32_t)ed, Rf_asReal(lambda), Rf_asInteger(K), REAL(W),
+                              NULL, NULL, NULL, NULL, &E, &iters, &Kout, NULL);
+  if (st != 0) { UNPROTECT(1); check(st); }
+  const char* nm[] = {"W", "E", "iters", "K"};
+  SEXP out = PROTECT(named_list(4, nm));
+  SET_VECTOR_ELT(out, 0, W);
+  SET_VECTOR_ELT(out, 1, Rf_ScalarReal(E));
+  SET_VECTOR_ELT(out, 2, Rf_ScalarInteger(iters));
+  SET_VECTOR_ELT(out, 3, Rf_ScalarInteger(Kout));
+  UNPROTECT(2);
+  return out;
+}
+
+/* .Call("rsoptsc_R_computeM", D, X, lambda)  ->  list(Z, E)   (R/SimilarityM.R:115-197) */
+SEXP rsoptsc_R_computeM(SEXP D, SEXP X, SEXP lambda) {
+  int64_t m, n, dr, dc;
+  dims(X, &m, &n);
+  dims(D, &dr, &dc);
+  if (dr != n || dc != n) Rf_error("D must be n x n");
+  SEXP Z = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)n));
+  double E = 0; int32_t iters = 0, stop = 0;
+  int st = rsoptsc_computeM_dense_mask(REAL(D), REAL(X), m, n, Rf_asReal(lambda), REAL(Z), &E, &iters, &stop, NULL);
+  if (st != 0) { UNPROTECT(1); check(st); }
+  const char* nm[] = {"Z", "E"};
+  SEXP out = PROTECT(named_list(2, nm));
+  SET_VECTOR_ELT(out, 0, Z);
+  SET_VECTOR_ELT(out, 1, Rf_ScalarReal(E));
+  UNPROTECT(2);
+  return out;
+}
+
+/* .Call("rsoptsc_R_nmf", V, k)  ->  list(H = basis n x k, labels)   (R/Clustering.R:29-37) */
+SEXP rsoptsc_R_nmf(SEXP V, SEXP k) {
+  int64_t n, nc;
+  dims(V, &n, &nc);
+  if (n != nc) Rf_error("similarity matrix must be square");
+  const int kk = Rf_asInteger(k);
+  SEXP H = PROTECT(Rf_allocMatrix(REALSXP, (int)n, kk));
+  SEXP lab = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)n));
+  int32_t iters = 0;
+  int st = rsoptsc_nmf_lee(REAL(V), n, kk, 2000, REAL(H), NULL, (int32_t*)INTEGER(lab), &iters);
+  if (st != 0) { UNPROTECT(2); check(st); }
+  const char* nm[] = {"H", "labels"};
+  SEXP out = PROTECT(named_list(2, nm));
+  SET_VECTOR_ELT(out, 0, H);
+  SET_VECTOR_ELT(out, 1, lab);
+  UNPROTECT(3);
+  return out;
+}
+
+/* .Call("rsoptsc_R_get_components", S, tol) -> list(val, n_eigs)   (R/Clustering.R:96-105) */
+SEXP rsoptsc_R_get_components(SEXP S, SEXP tol) {
+  int64_t n, nc;
+  dims(S, &n, &nc);
+  SEXP val = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)n));
+  int32_t ne = 0;
+  int st = rsoptsc_get_components(REAL(S), n, Rf_asReal(tol), REAL(val), &ne);
+  if (st != 0) { UNPROTECT(1); check(st); }
+  const char* nm[] = {"val", "n_eigs"};
+  SEXP out = PROTECT(named_list(2, nm));
+  SET_VECTOR_ELT(out, 0, val);
+  SET_VECTOR_ELT(out, 1, Rf_ScalarInteger(ne));
+  UNPROTECT(2);
+  return out;
+}
+
+/* .Call("rsoptsc_R_count_clusters", S, tol, range_lo, range_hi, n_comp)
+ *   -> list(upper_bound, lower_bound, eigs = list(val, n_eigs))   (R/Clustering.R:61-83) */
+SEXP rsoptsc_R_count_clusters(SEXP S, SEXP tol, SEXP lo, SEXP hi, SEXP n_comp) {
+  int64_t n, nc;
+  dims(S, &n, &nc);
+  SEXP val = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)n));
+  int32_t up = 0, low = 0, ne = 0;
+  int st = rsoptsc_count_clusters(REAL(S), n, Rf_asReal(tol), Rf_asInteger(lo), Rf_asInteger(hi), Rf_asInteger(n_comp),
+                                  &up, &low, REAL(val), &ne);
+  if (st != 0) { UNPROTECT(1); check(st); }
+  const char* en[] = {"val", "n_eigs"};
+  SEXP eigs = PROTECT(named_list(2, en));
+  SET_VECTOR_ELT(eigs, 0, val);
+  SET_VECTOR_ELT(eigs, 1, Rf_ScalarInteger(ne));
+  const char* nm[] = {"upper_bound", "lower_bound", "eigs"};
+  SEXP out = PROTECT(named_list(3, nm));
+  SET_VECTOR_ELT(out, 0, Rf_ScalarInteger(up));
+  SET_VECTOR_ELT(out, 1, Rf_ScalarInteger(low));
+  SET_VECTOR_ELT(out, 2, eigs);
+  UNPROTECT(3);
+  return out;
+}
+
+static const R_CallMethodDef call_methods[] = {
+    {"rsoptsc_R_similarity", (DL_FUNC)&rsoptsc_R_similarity, 4},
+    {"rsoptsc_R_computeM", (DL_FUNC)&rsoptsc_R_computeM, 3},
+    {"rsoptsc_R_nmf", (DL_FUNC)&rsoptsc_R_nmf, 2},
+    {"rsoptsc_R_get_components", (DL_FUNC)&rsoptsc_R_get_components, 2},
+    {"rsoptsc_R_count_clusters", (DL_FUNC)&rsoptsc_R_count_clusters, 5},
+    {NULL, NULL, 0}};
+
+void R_init_RSoptSC(DllInfo* dll) {
+  R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
+  R_useDynamicSymbols(dll, FALSE);
+  rsoptsc_init(-1); /* one process per GPU: current device; failure surfaces on first call */
+}

@@ -4,6 +4,7 @@
 #include <unordered_map>
 
 #include "../../include/rsoptsc_b200.h"
+#include "gemm.h"
 #include "internal.h"
 
 namespace rs {
@@ -467,6 +468,55 @@ int rsoptsc_count_clusters(const double* S, int64_t n, double tol, int32_t range
     DevBuf<double> d((size_t)n * n);
     d.upload(S, (size_t)n * n, s);
     count_clusters(d.p, n, tol, range_lo, range_hi, n_comp, upper_bound, lower_bound, vals, n_eigs);
+  });
+}
+
+int rsoptsc_set_gemm_backend(int32_t backend) {
+  return guarded([&] {
+    RS_REQUIRE(backend == 0 || backend == 1, "gemm backend must be 0 (cublas) or 1 (ozaki)");
+    set_gemm_backend(backend);
+  });
+}
+int32_t rsoptsc_get_gemm_backend(void) { return gemm_backend(); }
+int rsoptsc_debug_gemm(int32_t op, const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K,
+                       int32_t backend, int32_t reps, double* ms_out) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(op >= 0 && op <= 3 && M > 0 && N > 0 && K > 0 && reps >= 1, "debug_gemm: bad arguments");
+    if (op == 0) N = M;
+    const size_t na = (size_t)M * K, nb = op == 0 ? 0 : (size_t)N * K, nc = (size_t)M * N;
+    DevBuf<double> a(na), b(std::max<size_t>(nb, 1)), c(nc);
+    a.upload(A, na, s);
+    if (nb) b.upload(B, nb, s);
+    const int saved = gemm_backend();
+    set_gemm_backend(backend);
+    cudaEvent_t e0, e1;
+    RS_CUDA(cudaEventCreate(&e0)); RS_CUDA(cudaEventCreate(&e1));
+    auto call = [&] {
+      switch (op) {
+        case 0: gram_AtA(a.p, K, M, c.p); break;
+        case 1: gemm_nn(a.p, b.p, c.p, M, N, K); break;
+        case 2: gemm_nt(a.p, b.p, c.p, M, N, K); break;
+        default: gemm_tn(a.p, b.p, c.p, M, N, K); break;
+      }
+    };
+    try {
+      call();  // warm-up (also sets function attributes)
+      RS_CUDA(cudaEventRecord(e0, s));
+      for (int r = 0; r < reps; ++r) call();
+      RS_CUDA(cudaEventRecord(e1, s));
+      RS_CUDA(cudaEventSynchronize(e1));
+    } catch (...) {
+      set_gemm_backend(saved);
+      throw;
+    }
+    set_gemm_backend(saved);
+    float ms = 0;
+    RS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms_out) *ms_out = ms / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    c.download(C, nc, s);
+    RS_CUDA(cudaStreamSynchronize(s));
   });
 }
 

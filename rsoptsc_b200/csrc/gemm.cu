@@ -1,11 +1,34 @@
-// Dense contractions.  Round-1 baseline: cuBLAS FP64 (DSYRK/DGEMM, ~35 TFLOP/s measured on
-// B200).  The tcgen05 split-integer path (gemm_ozaki.cu) replaces these where enabled.
+// Dense FP64(-equivalent) contractions of the path: Gram A^T A and the two reconstruction
+// GEMMs of the SVT (a4), the centred Gram of the PCA (a2).
+//   backend "ozaki"  : tcgen05 kind::i8 split-integer GEMM (gemm_ozaki.cu), FP64-equivalent
+//   backend "cublas" : cuBLAS DSYRK/DGEMM (library baseline, ~35 TFLOP/s measured on B200)
+// RSOPTSC_GEMM=cublas|ozaki selects; small problems always take the library call.
 #include "gemm.h"
 #include "internal.h"
 
 namespace rs {
 
+void ozaki_gram_AtA(const double* A, int64_t rows, int64_t cols, double* G);
+void ozaki_gemm_nn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
+void ozaki_gemm_nt(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
+void ozaki_gemm_tn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
+
+static int g_backend = -1;  // 0 cublas, 1 ozaki
+int gemm_backend() {
+  if (g_backend < 0) {
+    const char* e = getenv("RSOPTSC_GEMM");
+    g_backend = (e && std::string(e) == "ozaki") ? 1 : 0;
+  }
+  return g_backend;
+}
+void set_gemm_backend(int b) { g_backend = b; }
+
+static bool use_ozaki(int64_t M, int64_t N, int64_t K) {
+  return gemm_backend() == 1 && M >= 512 && N >= 512 && K >= 512 && M <= 65535 && N <= 65535;
+}
+
 void gram_AtA(const double* A, int64_t rows, int64_t cols, double* G) {
+  if (use_ozaki(cols, cols, rows)) return ozaki_gram_AtA(A, rows, cols, G);
   const double one = 1.0, zero = 0.0;
   RS_CUBLAS(cublasDsyrk(ctx().cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, (int)cols, (int)rows, &one, A, (int)rows,
                         &zero, G, (int)cols));
@@ -16,16 +39,19 @@ void gram_AAt(const double* A, int64_t rows, int64_t cols, double* G) {
                         &zero, G, (int)rows));
 }
 void gemm_nn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K) {
+  if (use_ozaki(M, N, K)) return ozaki_gemm_nn(A, B, C, M, N, K);
   const double one = 1.0, zero = 0.0;
   RS_CUBLAS(cublasDgemm(ctx().cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)M, (int)N, (int)K, &one, A, (int)M, B, (int)K,
                         &zero, C, (int)M));
 }
 void gemm_nt(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K) {
+  if (use_ozaki(M, N, K)) return ozaki_gemm_nt(A, B, C, M, N, K);
   const double one = 1.0, zero = 0.0;
   RS_CUBLAS(cublasDgemm(ctx().cublas, CUBLAS_OP_N, CUBLAS_OP_T, (int)M, (int)N, (int)K, &one, A, (int)M, B, (int)N,
                         &zero, C, (int)M));
 }
 void gemm_tn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K) {
+  if (use_ozaki(M, N, K)) return ozaki_gemm_tn(A, B, C, M, N, K);
   const double one = 1.0, zero = 0.0;
   RS_CUBLAS(cublasDgemm(ctx().cublas, CUBLAS_OP_T, CUBLAS_OP_N, (int)M, (int)N, (int)K, &one, A, (int)K, B, (int)K,
                         &zero, C, (int)M));

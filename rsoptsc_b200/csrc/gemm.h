@@ -4,6 +4,8 @@
 #include "common.h"
 
 namespace rs {
+int gemm_backend();            // 0 cuBLAS FP64, 1 tcgen05 split-integer (Ozaki)
+void set_gemm_backend(int b);
 // G (cols x cols, lower triangle valid) = A^T A,  A: rows x cols
 void gram_AtA(const double* A, int64_t rows, int64_t cols, double* G);
 // G (rows x rows, lower triangle valid) = A A^T

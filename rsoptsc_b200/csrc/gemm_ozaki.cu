@@ -1,0 +1,467 @@
+// FP64-equivalent dense contractions on the 5th-generation tensor cores (tcgen05, kind::i8).
+//
+// tcgen05.mma has no f64 kind and FP32 accumulation cannot reach the accuracy the Gram route of
+// the SVT needs.  The Ozaki split-integer scheme does: every operand row is
+// scaled by a power of two and cut into S signed 7-bit slices (int8), all slice-pair products
+// are EXACT in the int32 TMEM accumulators, and the FP64 result is the power-of-two weighted sum
+// of the group sums  sum_{t+u=p} Qa_t Qb_u^T  (p = 2..S+1; lower-order pairs are below 2^-7S).
+//
+// Kernel shape (one CTA per SM, persistent over 128 x 128 output tiles):
+//   warp 0      TMA producer: per 32-byte k-block ONE 3-D box per operand brings all S slices of
+//               the A rows and B rows ([slice][row][32 B], SWIZZLE_32B), so every slice is fetched
+//               once per k-block and reused by all its pairs (4.5x less L2->SM traffic than
+//               streaming the 36 pair-GEMMs one after another)
+//   warp 1      MMA issuer (one elected thread): tcgen05.mma.kind::i8 M128 N128 K32, the S/2 group
+//               accumulators of a pass live side by side in TMEM (4 x 128 columns = 512)
+//   warps 2-5   epilogue: tcgen05.ld, int32 -> FP64, scale by 2^(exA_i + exB_j - 7p), read-modify-write C
+// Two passes per tile: groups p > S/2+1 (need all slices), then the S/2 low groups (slices 1..S/2).
+#include <cuda.h>
+
+#include "gemm.h"
+#include "internal.h"
+
+namespace rs {
+namespace oz {
+
+constexpr int BM = 128, BN = 128, BK = 32;  // BK bytes == int8 elements per k-block == UMMA K
+constexpr int MAXS = 8;
+constexpr int STAGES = 3;
+constexpr int SLICE_TILE = BM * BK;               // 4 KB: one slice of one operand in a stage
+constexpr int OPER_BYTES = MAXS * SLICE_TILE;     // 32 KB
+constexpr int STAGE_BYTES = 2 * OPER_BYTES;       // 64 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int THREADS = 192;
+constexpr int ROWPAD = 128;
+
+struct Params {
+  double* C;
+  const int* exA;
+  const int* exB;
+  const int2* tiles;
+  int num_tiles, M, N, ldc, kblocks, S, accumulate;
+};
+
+// ---- PTX helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1ll << 28)) __trap();  // a pipeline bug must fault, not hang the GPU
+  }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile, SWIZZLE_32B: rows at a 32-byte pitch, 8-row atoms of 256 B (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 6ull << 61;
+  return d;
+}
+// kind::i8 instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N = 128, M = 128
+__device__ __forceinline__ uint32_t make_idesc() {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+#define TMEM_LD_32x32b_X32(taddr, r)                                                                          \
+  asm volatile(                                                                                               \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                               \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, " \
+      "%22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                                             \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),       \
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), \
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),            \
+        "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),            \
+        "=r"(r[30]), "=r"(r[31])                                                                              \
+      : "r"(taddr)                                                                                            \
+      : "memory")
+
+__device__ __forceinline__ double pow2(int e) {
+  e = max(-1022, min(1023, e));
+  return __hiloint2double((e + 1023) << 20, 0);
+}
+
+// pass 0: groups p = S/2+2 .. S+1 (all slices); pass 1: groups p = 2 .. S/2+1 (slices 1..S/2)
+__device__ __forceinline__ void pass_groups(int S, int pass, int& p_lo, int& p_hi) {
+  if (pass == 0) { p_lo = S / 2 + 2; p_hi = S + 1; } else { p_lo = 2; p_hi = S / 2 + 1; }
+}
+// k-blocks per int32 accumulation unit: npairs * K * 127^2 < 2^31
+__device__ __host__ __forceinline__ int max_kblocks(int S) { return (133000 / S) / BK; }
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_ozaki_gemm(const __grid_constant__ CUtensorMap tmA_full, const __grid_constant__ CUtensorMap tmA_half,
+             const __grid_constant__ CUtensorMap tmB_full, const __grid_constant__ CUtensorMap tmB_half, Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - raw);
+  const uint32_t bars = base + STAGES * STAGE_BYTES;
+  // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full, tmem_empty ; then the TMEM base address
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  const uint32_t tmem_full = bars + 8u * (2 * STAGES);
+  const uint32_t tmem_empty = bars + 8u * (2 * STAGES + 1);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = P.S;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32((const void*)tmem_slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int kb_total = P.kblocks;
+  const int kb_unit = max_kblocks(S);
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ti = blockIdx.x; ti < P.num_tiles; ti += gridDim.x) {
+        const int2 t = P.tiles[ti];
+        for (int kb0 = 0; kb0 < kb_total; kb0 += kb_unit) {
+          const int kb1 = min(kb_total, kb0 + kb_unit);
+          for (int pass = 0; pass < 2; ++pass) {
+            const int nsl = pass == 0 ? S : S / 2;
+            const uint32_t bytes = 2u * nsl * SLICE_TILE;
+            for (int kb = kb0; kb < kb1; ++kb) {
+              mbar_wait(empty_bar(stage), phase ^ 1);
+              mbar_expect_tx(full_bar(stage), bytes);
+              const uint32_t sa = base + stage * STAGE_BYTES;
+              tma_load_3d(sa, pass == 0 ? &tmA_full : &tmA_half, full_bar(stage), kb * BK, t.x * BM, 0);
+              tma_load_3d(sa + OPER_BYTES, pass == 0 ? &tmB_full : &tmB_half, full_bar(stage), kb * BK, t.y * BN, 0);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc();
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int ti = blockIdx.x; ti < P.num_tiles; ti += gridDim.x) {
+        for (int kb0 = 0; kb0 < kb_total; kb0 += kb_unit) {
+          const int kb1 = min(kb_total, kb0 + kb_unit);
+          for (int pass = 0; pass < 2; ++pass) {
+            int p_lo, p_hi;
+            pass_groups(S, pass, p_lo, p_hi);
+            mbar_wait(tmem_empty, acc_phase ^ 1);  // epilogue has drained the previous unit
+            tc_fence_after();
+            for (int kb = kb0; kb < kb1; ++kb) {
+              mbar_wait(full_bar(stage), phase);
+              tc_fence_after();
+              const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + OPER_BYTES;
+              for (int p = p_lo; p <= p_hi; ++p) {
+                const uint32_t d = tmem_base + (uint32_t)(p - p_lo) * BN;
+                for (int tt = 1; tt < p; ++tt) {
+                  const int uu = p - tt;
+                  if (tt > S || uu > S) continue;
+                  umma_i8(d, smem_desc_sw32(sa + (tt - 1) * SLICE_TILE), smem_desc_sw32(sb + (uu - 1) * SLICE_TILE), idesc,
+                          (kb > kb0 || tt > 1) ? 1u : 0u);
+                }
+              }
+              umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tmem_full);           // accumulators of this unit are complete
+            acc_phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =================
+    const int q = warp & 3;
+    uint32_t acc_phase = 0;
+    for (int ti = blockIdx.x; ti < P.num_tiles; ti += gridDim.x) {
+      const int2 t = P.tiles[ti];
+      const int row = t.x * BM + q * 32 + lane;
+      const int exa = row < P.M ? P.exA[row] : 0;
+      bool first = true;
+      for (int kb0 = 0; kb0 < kb_total; kb0 += kb_unit) {
+        for (int pass = 0; pass < 2; ++pass) {
+          int p_lo, p_hi;
+          pass_groups(S, pass, p_lo, p_hi);
+          mbar_wait(tmem_full, acc_phase);
+          tc_fence_after();
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            double sum[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[j] = 0.0;
+            for (int p = p_hi; p >= p_lo; --p) {  // smallest contributions first
+              uint32_t r[32];
+              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((p - p_lo) * BN + c0);
+              TMEM_LD_32x32b_X32(taddr, r);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              const double w = pow2(-7 * p);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sum[j] += (double)(int)r[j] * w;
+            }
+            if (row < P.M) {
+#pragma unroll 4
+              for (int j = 0; j < 32; ++j) {
+                const int col = t.y * BN + c0 + j;
+                if (col < P.N) {
+                  const double v = sum[j] * pow2(exa + P.exB[col]);
+                  double* dst = P.C + (size_t)row + (size_t)col * P.ldc;
+                  *dst = (first && !P.accumulate) ? v : (*dst + v);
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty);
+          acc_phase ^= 1;
+          first = false;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
+// ---- slicing ------------------------------------------------------------------------------------
+// Operand row r, contraction index k.  contig: x = X[k + r*ld] (K runs down a column of X);
+// otherwise x = X[r + k*ld].  Q[t][r][k] (int8, k contiguous, padded with zeros).
+__global__ void k_rowmax_contig(const double* __restrict__ X, int64_t ld, int R, int K, int* __restrict__ ex) {
+  __shared__ double sm[8];
+  const int r = blockIdx.x;
+  double mx = 0;
+  for (int k = threadIdx.x; k < K; k += 256) mx = fmax(mx, fabs(X[(int64_t)k + (int64_t)r * ld]));
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) mx = fmax(mx, sm[w]);
+    int e = 0;
+    if (mx > 0 && isfinite(mx)) frexp(mx, &e);  // mx = f * 2^e, f in [0.5, 1)
+    ex[r] = e;
+  }
+}
+__global__ void k_rowmax_strided(const double* __restrict__ X, int64_t ld, int R, int K, int* __restrict__ ex) {
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= R) return;
+  double mx = 0;
+  for (int k = 0; k < K; ++k) mx = fmax(mx, fabs(X[(int64_t)r + (int64_t)k * ld]));
+  int e = 0;
+  if (mx > 0 && isfinite(mx)) frexp(mx, &e);
+  ex[r] = e;
+}
+__device__ __forceinline__ void slice_value(double x, int e, int S, int8_t* out) {
+  double v = x * pow2(-e);  // |v| < 1, exact
+#pragma unroll
+  for (int t = 0; t < MAXS; ++t) {
+    if (t >= S) break;
+    v *= 128.0;
+    double qd = (t == S - 1) ? rint(v) : trunc(v);
+    qd = fmin(127.0, fmax(-127.0, qd));
+    out[t] = (int8_t)(int)qd;
+    v -= qd;
+  }
+}
+__global__ void k_slice_contig(const double* __restrict__ X, int64_t ld, int R, int K, const int* __restrict__ ex, int S,
+                               int64_t Rp, int64_t Kp, int8_t* __restrict__ Q) {
+  const int r = blockIdx.y;
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= K) return;
+  int8_t q[MAXS];
+  slice_value(X[(int64_t)k + (int64_t)r * ld], ex[r], S, q);
+  for (int t = 0; t < S; ++t) Q[((int64_t)t * Rp + r) * Kp + k] = q[t];
+}
+// 32 rows x 32 k per block through shared memory so that both the FP64 reads (along r) and the
+// int8 writes (along k) are contiguous
+__global__ void k_slice_strided(const double* __restrict__ X, int64_t ld, int R, int K, const int* __restrict__ ex,
+                                int S, int64_t Rp, int64_t Kp, int8_t* __restrict__ Q) {
+  __shared__ int8_t tile[MAXS][32][33];
+  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  for (int kk = threadIdx.y; kk < 32; kk += blockDim.y) {
+    const int r = r0 + threadIdx.x, k = k0 + kk;
+    int8_t q[MAXS];
+#pragma unroll
+    for (int t = 0; t < MAXS; ++t) q[t] = 0;
+    if (r < R && k < K) slice_value(X[(int64_t)r + (int64_t)k * ld], ex[r], S, q);
+    for (int t = 0; t < S; ++t) tile[t][threadIdx.x][kk] = q[t];
+  }
+  __syncthreads();
+  for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+    const int r = r0 + rr, k = k0 + threadIdx.x;
+    if (r < R && k < K)
+      for (int t = 0; t < S; ++t) Q[((int64_t)t * Rp + r) * Kp + k] = tile[t][rr][threadIdx.x];
+  }
+}
+
+struct Operand {
+  DevBuf<int8_t> Q;
+  DevBuf<int> ex;
+  int64_t R = 0, K = 0, Rp = 0, Kp = 0;
+  int S = 0;
+};
+
+static void slice_operand(const double* X, int64_t ld, int64_t R, int64_t K, bool contig, int S, Operand& op) {
+  op.R = R; op.K = K; op.S = S;
+  op.Rp = (R + ROWPAD - 1) / ROWPAD * ROWPAD;
+  op.Kp = (K + BK - 1) / BK * BK;
+  op.Kp = (op.Kp + 127) / 128 * 128;  // keep rows 128-byte aligned for TMA strides
+  op.Q.alloc((size_t)S * op.Rp * op.Kp);
+  op.ex.alloc(op.Rp);
+  RS_CUDA(cudaMemsetAsync(op.Q.p, 0, op.Q.n, ctx().stream));
+  RS_CUDA(cudaMemsetAsync(op.ex.p, 0, sizeof(int) * op.Rp, ctx().stream));
+  if (contig) {
+    RS_LAUNCH(k_rowmax_contig, (unsigned)R, 256, 0, X, ld, (int)R, (int)K, op.ex.p);
+    dim3 grid((unsigned)cdiv(K, 256), (unsigned)R);
+    RS_REQUIRE(R <= 65535, "ozaki: operand has too many rows for this launch shape");
+    RS_LAUNCH(k_slice_contig, grid, 256, 0, X, ld, (int)R, (int)K, op.ex.p, S, op.Rp, op.Kp, op.Q.p);
+  } else {
+    RS_LAUNCH(k_rowmax_strided, (unsigned)cdiv(R, 256), 256, 0, X, ld, (int)R, (int)K, op.ex.p);
+    dim3 grid((unsigned)cdiv(K, 32), (unsigned)cdiv(R, 32)), block(32, 8);
+    RS_REQUIRE(cdiv(R, 32) <= 65535, "ozaki: operand has too many rows for this launch shape");
+    RS_LAUNCH(k_slice_strided, grid, block, 0, X, ld, (int)R, (int)K, op.ex.p, S, op.Rp, op.Kp, op.Q.p);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    RS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    RS_REQUIRE(p != nullptr && q == cudaDriverEntryPointSuccess, "ozaki: cuTensorMapEncodeTiled not available");
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+static CUtensorMap make_map(const Operand& op, int depth) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {(cuuint64_t)op.Kp, (cuuint64_t)op.Rp, (cuuint64_t)op.S};
+  cuuint64_t strides[2] = {(cuuint64_t)op.Kp, (cuuint64_t)op.Kp * op.Rp};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BM, (cuuint32_t)depth};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)op.Q.p, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RS_REQUIRE(r == CUDA_SUCCESS, "ozaki: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return m;
+}
+
+static void run(const Operand& a, const Operand& b, double* C, int64_t M, int64_t N, int64_t ldc, bool lower_only,
+                bool accumulate) {
+  RS_REQUIRE(a.Kp == b.Kp && a.S == b.S, "ozaki: operand mismatch");
+  const int tm = (int)cdiv(M, BM), tn = (int)cdiv(N, BN);
+  std::vector<int2> tiles;
+  for (int j = 0; j < tn; ++j)
+    for (int i = 0; i < tm; ++i)
+      if (!lower_only || (int64_t)j * BN <= (int64_t)i * BM + BM - 1) tiles.push_back(make_int2(i, j));
+  DevBuf<int2> d_tiles(tiles.size());
+  RS_CUDA(cudaMemcpyAsync(d_tiles.p, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, ctx().stream));
+  Params P;
+  P.C = C; P.exA = a.ex.p; P.exB = b.ex.p; P.tiles = d_tiles.p; P.num_tiles = (int)tiles.size();
+  P.M = (int)M; P.N = (int)N; P.ldc = (int)ldc; P.kblocks = (int)(a.Kp / BK); P.S = a.S; P.accumulate = accumulate ? 1 : 0;
+  const CUtensorMap mAf = make_map(a, a.S), mAh = make_map(a, a.S / 2), mBf = make_map(b, b.S), mBh = make_map(b, b.S / 2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RS_CUDA(cudaFuncSetAttribute(k_ozaki_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = std::min<int>((int)tiles.size(), ctx().sm_count);
+  k_ozaki_gemm<<<grid, THREADS, SMEM_BYTES, ctx().stream>>>(mAf, mAh, mBf, mBh, P);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  RS_KERNEL_CHECK();
+  RS_CUDA(cudaStreamSynchronize(ctx().stream));  // d_tiles and the operands are released by the callers
+}
+
+}  // namespace oz
+
+static int ozaki_slices() {
+  static int s = -1;
+  if (s < 0) {
+    const char* e = getenv("RSOPTSC_OZAKI_SLICES");
+    s = e ? atoi(e) : 8;
+    if (s != 4 && s != 6 && s != 8) s = 8;
+  }
+  return s;
+}
+
+void ozaki_gram_AtA(const double* A, int64_t rows, int64_t cols, double* G) {
+  oz::Operand op;
+  oz::slice_operand(A, rows, cols, rows, /*contig=*/true, ozaki_slices(), op);
+  oz::run(op, op, G, cols, cols, cols, /*lower_only=*/true, false);
+}
+void ozaki_gemm_nn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K) {
+  oz::Operand a, b;
+  oz::slice_operand(A, M, M, K, /*contig=*/false, ozaki_slices(), a);
+  oz::slice_operand(B, K, N, K, /*contig=*/true, ozaki_slices(), b);
+  oz::run(a, b, C, M, N, M, false, false);
+}
+void ozaki_gemm_nt(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K) {
+  oz::Operand a, b;
+  oz::slice_operand(A, M, M, K, /*contig=*/false, ozaki_slices(), a);
+  oz::slice_operand(B, N, N, K, /*contig=*/false, ozaki_slices(), b);
+  oz::run(a, b, C, M, N, M, false, false);
+}
+void ozaki_gemm_tn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K) {
+  oz::Operand a, b;
+  oz::slice_operand(A, K, M, K, /*contig=*/true, ozaki_slices(), a);
+  oz::slice_operand(B, K, N, K, /*contig=*/true, ozaki_slices(), b);
+  oz::run(a, b, C, M, N, M, false, false);
+}
+
+}  // namespace rs

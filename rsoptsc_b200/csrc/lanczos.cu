@@ -15,7 +15,7 @@
 namespace rs {
 
 // ---- host: symmetric tridiagonal QL with implicit shifts (EISPACK tql2 scheme) -----------
-void tridiag_eig(std::vector<double>& d, std::vector<double>& e_in, std::vector<double>* Zv) {
+void tridiag_eig(std::vector<double>& d, std::vector<double>& e_in, std::vector<double>* Zv, bool last_row_only) {
   const int n = (int)d.size();
   if (n == 0) return;
   std::vector<double> e(n, 0.0);
@@ -23,7 +23,12 @@ void tridiag_eig(std::vector<double>& d, std::vector<double>& e_in, std::vector<
   std::vector<double> dummy;
   const bool wantv = Zv != nullptr;
   std::vector<double>& V = wantv ? *Zv : dummy;
-  if (wantv) {
+  // last_row_only: V (length n) carries only the last row of the eigenvector matrix -- all a
+  // Lanczos residual estimate needs -- so the whole solve is O(n^2) instead of O(n^3).
+  if (wantv && last_row_only) {
+    V.assign((size_t)n, 0.0);
+    V[n - 1] = 1.0;
+  } else if (wantv) {
     V.assign((size_t)n * n, 0.0);
     for (int i = 0; i < n; ++i) V[(size_t)i * n + i] = 1.0;  // column-major: V[row + col*n]
   }
@@ -65,7 +70,11 @@ void tridiag_eig(std::vector<double>& d, std::vector<double>& e_in, std::vector<
           c = p / r;
           p = c * d[i] - s * g;
           d[i + 1] = h + s * (c * g + s * d[i]);
-          if (wantv) {
+          if (wantv && last_row_only) {
+            h = V[i + 1];
+            V[i + 1] = s * V[i] + c * h;
+            V[i] = c * V[i] - s * h;
+          } else if (wantv) {
             double* vi = &V[(size_t)i * n];
             double* vi1 = &V[(size_t)(i + 1) * n];
             for (int k = 0; k < n; ++k) {
@@ -92,7 +101,8 @@ void tridiag_eig(std::vector<double>& d, std::vector<double>& e_in, std::vector<
     if (k != i) {
       d[k] = d[i];
       d[i] = p;
-      if (wantv)
+      if (wantv && last_row_only) std::swap(V[i], V[k]);
+      else if (wantv)
         for (int r = 0; r < n; ++r) std::swap(V[(size_t)i * n + r], V[(size_t)k * n + r]);
     }
   }
@@ -286,10 +296,10 @@ void Lanczos::advance(int more) {
   }
 }
 
-void Lanczos::ritz(std::vector<double>& theta, std::vector<double>& S) const {
+void Lanczos::ritz(std::vector<double>& theta, std::vector<double>& S, bool last_row_only) const {
   theta = alpha;
   std::vector<double> e(beta.begin(), beta.begin() + std::max(0, steps - 1));
-  tridiag_eig(theta, e, &S);
+  tridiag_eig(theta, e, &S, last_row_only);
 }
 
 // Y[:, c] = Q[:, 0..steps) * S[:, sel[c]]
@@ -333,12 +343,12 @@ double spectral_norm(const double* d_M, int64_t rows, int64_t cols, double rel_t
     lz.advance(lz.steps == 0 ? 24 : 16);
     if (lz.steps == 0) return 0.0;
     std::vector<double> theta, S;
-    lz.ritz(theta, S);
+    lz.ritz(theta, S, /*last_row_only=*/true);
     const int k = lz.steps;
     cur = theta[k - 1];
     if (!(cur > 0)) return 0.0;
     // residual bound of the top Ritz pair: |beta_k * s_k|
-    const double resid = std::fabs(lz.beta[k - 1] * S[(size_t)(k - 1) * k + (k - 1)]);
+    const double resid = std::fabs(lz.beta[k - 1] * S[k - 1]);
     // Ritz value error <= min(resid, resid^2 / gap); gap estimated from the top two Ritz values
     const double gap = k >= 2 ? std::max(cur - theta[k - 2], 1e-300) : cur;
     const double err = std::min(resid, resid * resid / gap);

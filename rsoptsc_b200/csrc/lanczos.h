@@ -27,7 +27,7 @@ struct Lanczos {  // symmetric Lanczos with full reorthogonalisation on a device
   void init(int64_t dim, int max_steps, std::function<void(const double*, double*)> op);
   void advance(int more);
   // eigen-decomposition of the current tridiagonal: theta ascending, S steps x steps column-major
-  void ritz(std::vector<double>& theta, std::vector<double>& S) const;
+  void ritz(std::vector<double>& theta, std::vector<double>& S, bool last_row_only = false) const;
   // d_Y (dim x sel.size(), column-major) = Q * S[:, sel]
   void ritz_vectors(const std::vector<double>& S, const std::vector<int>& sel, double* d_Y);
 };

@@ -221,17 +221,16 @@ static void nndsvd_seed(const Compressed& csr, const Compressed& csc, int64_t n,
   int next = std::min(cap, std::max(2 * k + 24, 48));
   while (true) {
     lz.advance(next - lz.steps);
-    lz.ritz(theta, S);
+    lz.ritz(theta, S, /*last_row_only=*/true);
     const int st = lz.steps;
     RS_REQUIRE(st >= k, "nmf: matrix rank is below the requested factorisation rank");
     const double top = theta[st - 1];
     bool conv = true;
     for (int i = 0; i < k && conv; ++i) {
-      const int col = st - 1 - i;
-      const double resid = std::fabs(lz.beta[st - 1] * S[(size_t)col * st + (st - 1)]);
+      const double resid = std::fabs(lz.beta[st - 1] * S[st - 1 - i]);
       conv = resid <= 1e-13 * top;
     }
-    if (conv || lz.exhausted || st >= lz.max_steps) break;
+    if (conv || lz.exhausted || st >= lz.max_steps) { lz.ritz(theta, S); break; }
     next = std::min(lz.max_steps, st + std::max(32, st / 3));
   }
   const int st = lz.steps;

@@ -54,6 +54,23 @@ def test_fails_loudly_without_gpu(lib):
         api.normalize(x)
 
 
+def test_r_shim_compiles_against_stub(tmp_path):
+    # R headers are absent here: compile-check the .Call shim against the minimal stub only
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    out = tmp_path / "shim.o"
+    r = subprocess.run(["gcc", "-std=c99", "-DRSOPTSC_STUB_R", "-I", os.path.join(ROOT, "r"), "-I",
+                        os.path.join(ROOT, "include"), "-c", os.path.join(ROOT, "r", "rsoptsc_shim.c"), "-o", str(out)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # every C-ABI function the shim calls is declared in the header
+    src = open(os.path.join(ROOT, "r", "rsoptsc_shim.c")).read()
+    used = set(re.findall(r"\b(rsoptsc_(?!R_)[a-z_A-Z0-9]+)\s*\(", src))
+    assert used and used <= set(_declared())
+
+
 def test_host_tridiag_eig(lib):
     rng = np.random.default_rng(0)
     for k in (1, 2, 7, 64, 300):
