@@ -184,3 +184,81 @@ def test_cluster_cells_with_inferred_count(joost):
     r = api.ClusterCells(joost["S"], n_comp=3)
     assert r["ensemble"]["upper_bound"] == 9
     assert np.array_equal(r["labels"], joost["labels"])
+
+
+# ---- full-size (BASELINE.json configs[1]) size-independent properties -------------------------------
+def test_full_size_properties_config2():
+    """10,000 cells x 2,000 genes: the oracle would need hours, so check properties the domain offers:
+    mask respected, W symmetric non-negative with <= 2nK non-zeros, E == ||X - XZ||_F recomputed on
+    the host from the returned sparse W support, NMF basis columns sum to 1, labels in range, and
+    the planted populations are recovered (ARI)."""
+    from rsoptsc_b200.synthetic import synthetic_lognorm
+    m, n, k = 2000, 10000, 10
+    data, planted = synthetic_lognorm(m, n, seed=0)
+    r = api.SimilarityM(0.5, data, sparse=True)
+    W = r["W"]
+    K = r["K"]
+    assert 10 <= K <= 30 and 3 <= r["iters"] < 100
+    assert np.array_equal(W, W.T) and W.min() >= 0
+    nnz = np.count_nonzero(W)
+    assert n <= nnz <= 2 * n * K
+    rows, cols, vals = r["W_coo"]
+    assert len(vals) == (nnz + np.count_nonzero(np.diag(W))) // 2
+    assert np.array_equal(W[rows, cols], vals)
+    # neighbour structure: every non-zero of W is a kNN pair in one direction
+    idx = api.knn(r["nl_embedding"], K)
+    allowed = np.zeros((n, n), dtype=bool)
+    allowed[np.arange(n)[:, None], idx] = True
+    allowed |= allowed.T
+    assert not np.any((W > 0) & ~allowed)
+    c = api.ClusterCells(W, n_clusters=k)
+    assert np.allclose(c["H"].sum(axis=0), 1.0, atol=1e-10)
+    assert c["labels"].min() >= 1 and c["labels"].max() <= k
+    assert np.array_equal(c["labels"], np.argmax(c["H"], axis=1) + 1)
+    # agreement with the planted populations (pair-counting adjusted Rand index)
+    from scipy.special import comb
+    cont = np.zeros((k, planted.max() + 1))
+    np.add.at(cont, (c["labels"] - 1, planted), 1)
+    s_ij = comb(cont, 2).sum()
+    s_a, s_b = comb(cont.sum(1), 2).sum(), comb(cont.sum(0), 2).sum()
+    exp = s_a * s_b / comb(n, 2)
+    ari = (s_ij - exp) / (0.5 * (s_a + s_b) - exp)
+    assert ari > 0.5, ari
+
+
+def test_ozaki_gemm_matches_fp64():
+    """tcgen05 split-integer GEMM vs numpy FP64, error measured against |A||B| (DGEMM-style bound)."""
+    import ctypes as C
+    from rsoptsc_b200 import _lib
+    lib = _lib.init()
+    rng = np.random.default_rng(0)
+    dp = lambda a: a.ctypes.data_as(_lib.c_double_p)  # noqa: E731
+    for op, (M, N, K) in [(0, (700, 700, 900)), (1, (640, 768, 1000)), (2, (513, 900, 515)), (3, (1300, 600, 2100))]:
+        shapeA = (K, M) if op in (0, 3) else (M, K)
+        shapeB = {0: (K, M), 1: (K, N), 2: (N, K), 3: (K, N)}[op]
+        A = np.asfortranarray(rng.normal(size=shapeA) * np.exp(rng.normal(size=shapeA[1]) * 3)[None, :])
+        B = A if op == 0 else np.asfortranarray(rng.normal(size=shapeB) * np.exp(rng.normal(size=shapeB[0]) * 2)[:, None])
+        Nn = M if op == 0 else N
+        out = np.zeros((M, Nn), order="F")
+        _lib.check(lib.rsoptsc_debug_gemm(op, dp(A), dp(B), dp(out), M, Nn, K, 1, 1, None))
+        ref = {0: lambda: A.T @ A, 1: lambda: A @ B, 2: lambda: A @ B.T, 3: lambda: A.T @ B}[op]()
+        aa, bb = np.abs(A), np.abs(B)
+        bound = {0: lambda: aa.T @ aa, 1: lambda: aa @ bb, 2: lambda: aa @ bb.T, 3: lambda: aa.T @ bb}[op]()
+        err = np.abs(out - ref) / bound
+        if op == 0:
+            err = err[np.tril_indices(M)]
+        assert err.max() < 1e-13, (op, err.max())
+
+
+def test_computeM_with_ozaki_backend():
+    from rsoptsc_b200 import _lib
+    lib = _lib.init()
+    p = small_problem(300, 700, seed=21)
+    ref = O.computeM(O.mask_from_idx(p["idx"], 700), p["X"], 0.5, literal=False)
+    lib.rsoptsc_set_gemm_backend(1)
+    try:
+        got = api.computeM(None, p["X"], 0.5, idx=p["idx"])
+    finally:
+        lib.rsoptsc_set_gemm_backend(0)
+    assert got["iters"] == ref["iters"]
+    assert relF(got["Z"], ref["Z"]) < 1e-6
