@@ -17,7 +17,7 @@ static int g_backend = -1;  // 0 cublas, 1 ozaki
 int gemm_backend() {
   if (g_backend < 0) {
     const char* e = getenv("RSOPTSC_GEMM");
-    g_backend = (e && std::string(e) == "ozaki") ? 1 : 0;
+    g_backend = (e && std::string(e) == "cublas") ? 0 : 1;  // default: the tcgen05 path
   }
   return g_backend;
 }

@@ -69,7 +69,7 @@ double admm_residual_update(AdmmState& st, const Support& s, double mu, bool upd
 // ---- spectral norm (lanczos.cu) -----------------------------------------------------
 // Largest singular value of the column-major rows x cols matrix (Lanczos on the smaller Gram
 // operator, full reorthogonalisation).  rel_tol on the Ritz value.
-double spectral_norm(const double* d_M, int64_t rows, int64_t cols, double rel_tol = 1e-13);
+double spectral_norm(const double* d_M, int64_t rows, int64_t cols, double rel_tol = 2e-10);
 // Host: eigen-decomposition of a symmetric tridiagonal (d: k diag, e: k-1 off-diag).
 // On return d holds ascending eigenvalues, Zv (k x k column-major, may be null) eigenvectors.
 void tridiag_eig(std::vector<double>& d, std::vector<double>& e, std::vector<double>* Zv, bool last_row_only = false);

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <functional>
 
+#include "gemm.h"
 #include "internal.h"
 #include "lanczos.h"
 
@@ -325,22 +326,42 @@ void Lanczos::ritz_vectors(const std::vector<double>& S, const std::vector<int>&
 }
 
 // ---- spectral norm ------------------------------------------------------------------------
+// upper triangle <- lower triangle (column-major d x d)
+__global__ void k_mirror_lower(double* __restrict__ B, int64_t d) {
+  const int64_t j = blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x; i < j; i += (int64_t)gridDim.x * LT) B[i + j * d] = B[j + i * d];
+}
+
 double spectral_norm(const double* d_M, int64_t rows, int64_t cols, double rel_tol) {
   Phase ph("lanczos");
   if (rows == 0 || cols == 0) return 0.0;
-  DenseMatvec mv;
-  mv.init(d_M, rows, cols);
   const bool small_rows = rows <= cols;
   const int64_t d = small_rows ? rows : cols;
-  DevBuf<double> tmp(small_rows ? cols : rows);
+  DenseMatvec mv;
+  DevBuf<double> tmp, B;
   Lanczos lz;
-  lz.init(d, 320, [&](const double* v, double* w) {
-    if (small_rows) { mv.mul_t(v, tmp.p); mv.mul_n(tmp.p, w); }   // w = M (M^T v)
-    else            { mv.mul_n(v, tmp.p); mv.mul_t(tmp.p, w); }   // w = M^T (M v)
-  });
+  if (d <= 4096) {
+    // small side: form the d x d Gram once (one syrk) and iterate on it -- every Lanczos step is
+    // then one L2-resident symmetric matvec instead of two HBM streams over the m x n matrix
+    B.alloc((size_t)d * d);
+    if (small_rows) gram_AAt(d_M, rows, cols, B.p); else gram_AtA(d_M, rows, cols, B.p);
+    if (d > 1) {
+      dim3 grid((unsigned)std::min<int64_t>(cdiv(d, LT), 16), (unsigned)d);
+      RS_LAUNCH(k_mirror_lower, grid, LT, 0, B.p, d);
+    }
+    mv.init(B.p, d, d);
+    lz.init(d, 320, [&](const double* v, double* w) { mv.mul_t(v, w); });  // B symmetric: B^T v = B v
+  } else {
+    mv.init(d_M, rows, cols);
+    tmp.alloc(small_rows ? cols : rows);
+    lz.init(d, 320, [&](const double* v, double* w) {
+      if (small_rows) { mv.mul_t(v, tmp.p); mv.mul_n(tmp.p, w); }   // w = M (M^T v)
+      else            { mv.mul_n(v, tmp.p); mv.mul_t(tmp.p, w); }   // w = M^T (M v)
+    });
+  }
   double prev = -1, cur = 0;
   while (true) {
-    lz.advance(lz.steps == 0 ? 24 : 16);
+    lz.advance(lz.steps == 0 ? 32 : 16);
     if (lz.steps == 0) return 0.0;
     std::vector<double> theta, S;
     lz.ritz(theta, S, /*last_row_only=*/true);
@@ -349,11 +370,14 @@ double spectral_norm(const double* d_M, int64_t rows, int64_t cols, double rel_t
     if (!(cur > 0)) return 0.0;
     // residual bound of the top Ritz pair: |beta_k * s_k|
     const double resid = std::fabs(lz.beta[k - 1] * S[k - 1]);
-    // Ritz value error <= min(resid, resid^2 / gap); gap estimated from the top two Ritz values
-    const double gap = k >= 2 ? std::max(cur - theta[k - 2], 1e-300) : cur;
+    // Ritz value error <= min(resid, resid^2 / gap).  Ritz values within 0.1*rel_tol of the top are
+    // one cluster (their spread is below the requested accuracy); gap = distance to the rest.
+    double gap = cur;
+    for (int i = k - 2; i >= 0; --i)
+      if (cur - theta[i] > 0.1 * rel_tol * cur) { gap = cur - theta[i]; break; }
     const double err = std::min(resid, resid * resid / gap);
     const bool conv = err <= rel_tol * cur ||
-                      (prev > 0 && std::fabs(cur - prev) <= 0.1 * rel_tol * cur && resid <= 1e-6 * cur);
+                      (prev > 0 && std::fabs(cur - prev) <= 1e-3 * rel_tol * cur && resid <= 1e-5 * cur);
     if (conv || lz.exhausted || lz.steps >= lz.max_steps) break;
     prev = cur;
   }

@@ -234,10 +234,19 @@ def test_ozaki_gemm_matches_fp64():
     rng = np.random.default_rng(0)
     dp = lambda a: a.ctypes.data_as(_lib.c_double_p)  # noqa: E731
     for op, (M, N, K) in [(0, (700, 700, 900)), (1, (640, 768, 1000)), (2, (513, 900, 515)), (3, (1300, 600, 2100))]:
-        shapeA = (K, M) if op in (0, 3) else (M, K)
-        shapeB = {0: (K, M), 1: (K, N), 2: (N, K), 3: (K, N)}[op]
-        A = np.asfortranarray(rng.normal(size=shapeA) * np.exp(rng.normal(size=shapeA[1]) * 3)[None, :])
-        B = A if op == 0 else np.asfortranarray(rng.normal(size=shapeB) * np.exp(rng.normal(size=shapeB[0]) * 2)[:, None])
+        # wide dynamic range ACROSS output rows/columns (what the per-row power-of-two scaling of
+        # the split-integer scheme absorbs); entries along the contraction index are O(1)
+        sa, sb = np.exp(rng.normal(size=M) * 3), np.exp(rng.normal(size=N) * 2)
+        if op in (0, 3):
+            A = np.asfortranarray(rng.normal(size=(K, M)) * sa[None, :])
+        else:
+            A = np.asfortranarray(rng.normal(size=(M, K)) * sa[:, None])
+        if op == 0:
+            B = A
+        elif op == 2:
+            B = np.asfortranarray(rng.normal(size=(N, K)) * sb[:, None])
+        else:
+            B = np.asfortranarray(rng.normal(size=(K, N)) * sb[None, :])
         Nn = M if op == 0 else N
         out = np.zeros((M, Nn), order="F")
         _lib.check(lib.rsoptsc_debug_gemm(op, dp(A), dp(B), dp(out), M, Nn, K, 1, 1, None))
@@ -250,15 +259,19 @@ def test_ozaki_gemm_matches_fp64():
         assert err.max() < 1e-13, (op, err.max())
 
 
-def test_computeM_with_ozaki_backend():
+@pytest.mark.parametrize("backend", [0, 1])
+def test_computeM_with_both_gemm_backends(backend):
+    """n >= 512 so the SVT contractions take the tcgen05 split-integer path (backend 1) or cuBLAS
+    FP64 (backend 0); both must reproduce the oracle."""
     from rsoptsc_b200 import _lib
     lib = _lib.init()
     p = small_problem(300, 700, seed=21)
     ref = O.computeM(O.mask_from_idx(p["idx"], 700), p["X"], 0.5, literal=False)
-    lib.rsoptsc_set_gemm_backend(1)
+    prev = lib.rsoptsc_get_gemm_backend()
+    lib.rsoptsc_set_gemm_backend(backend)
     try:
         got = api.computeM(None, p["X"], 0.5, idx=p["idx"])
     finally:
-        lib.rsoptsc_set_gemm_backend(0)
+        lib.rsoptsc_set_gemm_backend(prev)
     assert got["iters"] == ref["iters"]
     assert relF(got["Z"], ref["Z"]) < 1e-6
