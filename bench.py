@@ -254,7 +254,28 @@ def main():
         # dominant kernel among the kernels this repo owns (cuSOLVER/cuBLAS phases reported in `phases`)
         own = [(p, v) for p, v in phases.items() if own_kernel_bytes(p, m, n, nnz)]
         roof = None
-        if own:
+        oz = phases.get("ozaki_gemm")
+        if oz and oz["ms"] > 0:
+            # dominant kernel this repo owns: the tcgen05 kind::i8 split-integer GEMM (Gram + the two
+            # reconstruction GEMMs of every SVT).  achieved = FP64-equivalent flops / device time;
+            # peak = int8 tensor peak (2 x measured dense bf16) / 36 slice-pair MMAs per FP64 MAC.
+            bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
+            bf16_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks.get("bf16_tflops_sustained") else \
+                "fallback (B200_PROFILING.md)"
+            lib = _lib.load()
+            flops = lib.rsoptsc_counter(b"ozaki_fp64_flops")
+            iops = lib.rsoptsc_counter(b"ozaki_int8_ops")
+            secs = oz["ms"] / 1e3
+            pairs = iops / max(flops, 1.0)
+            roof = {"kernel": "k_ozaki_gemm<8> (tcgen05.mma kind::i8, FP64-equivalent)", "bound": "tensor",
+                    "achieved": flops / secs / 1e12, "peak": 2.0 * bf16 / pairs, "unit": "TFLOP/s",
+                    "frac": (flops / secs / 1e12) / (2.0 * bf16 / pairs), "traffic": None,
+                    "int8_tops_achieved": iops / secs / 1e12, "int8_tops_peak": 2.0 * bf16,
+                    "peak_source": "2 x %s (int8 runs at twice the bf16 rate) / %d int8 slice-pair MMAs per FP64 MAC"
+                                   % (bf16_src, round(pairs)),
+                    "share_of_step": secs / t_dev, "launches": oz["calls"],
+                    "cublas_fp64_reference_tflops": 35.6}
+        elif own:
             name, v = max(own, key=lambda kv: kv[1]["ms"])
             per_launch_s = v["ms"] / 1e3 / max(v["calls"], 1)
             achieved = own_kernel_bytes(name, m, n, nnz) / per_launch_s / 1e9

@@ -48,6 +48,10 @@ int rsoptsc_timers_reset(void);
 int rsoptsc_timers_enable(int on);
 /* Caller-defined device timer (CUDA events on the library stream) accumulated under `name`;
  * read back with rsoptsc_phase_ms(name).  bench.py brackets every timed step with these. */
+/* Work counters accumulated since the last rsoptsc_timers_reset():
+ *   "ozaki_fp64_flops"  FP64-equivalent flops (2 per output MAC) executed by the tcgen05 GEMM
+ *   "ozaki_int8_ops"    int8 tensor ops (2 per slice-pair MAC) the same launches issued      */
+double rsoptsc_counter(const char* name);
 /* i-th phase name seen so far, NULL past the end (enumeration for reports). */
 const char* rsoptsc_phase_name(int32_t i);
 int rsoptsc_timer_begin(const char* name);
@@ -141,7 +145,8 @@ int rsoptsc_count_clusters(const double* S, int64_t n, double tol, int32_t range
                            int32_t* lower_bound, double* vals, int32_t* n_eigs);
 
 /* ---- dense contraction backends (a4 Gram / reconstruction GEMMs) --------------------- */
-/* backend: 0 = cuBLAS FP64 (library baseline), 1 = tcgen05 split-integer (Ozaki) GEMM. */
+/* backend: 0 = cuBLAS FP64 (library baseline), 1 = tcgen05 split-integer (Ozaki) GEMM for
+ * contractions with every dimension >= 1536 (default), 2 = Ozaki wherever legal (>= 256). */
 int rsoptsc_set_gemm_backend(int32_t backend);
 int32_t rsoptsc_get_gemm_backend(void);
 /* One contraction on host buffers (column-major), for parity tests and kernel benchmarks:

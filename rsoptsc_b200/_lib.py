@@ -25,6 +25,7 @@ SIGNATURES = {
     "rsoptsc_timers_reset": (C.c_int, []),
     "rsoptsc_timers_enable": (C.c_int, [C.c_int]),
     "rsoptsc_phase_name": (C.c_char_p, [C.c_int32]),
+    "rsoptsc_counter": (C.c_double, [C.c_char_p]),
     "rsoptsc_timer_begin": (C.c_int, [C.c_char_p]),
     "rsoptsc_timer_end": (C.c_int, [C.c_char_p]),
     "rsoptsc_dev_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),

@@ -72,6 +72,8 @@ Phase::~Phase() {
   g_phases[id].calls++;
 }
 static std::unordered_map<std::string, cudaEvent_t> g_open_timers;
+static std::unordered_map<std::string, double> g_counters;
+void add_counter(const char* name, double v) { g_counters[name] += v; }
 static void resolve_phases() {
   if (!g_ctx.initialized) return;
   cudaStreamSynchronize(g_ctx.stream);
@@ -127,7 +129,12 @@ int rsoptsc_timers_enable(int on) { g_timers_on = on != 0; return 0; }
 int rsoptsc_timers_reset(void) {
   resolve_phases();
   for (auto& p : g_phases) { p.ms = 0; p.calls = 0; }
+  g_counters.clear();
   return 0;
+}
+double rsoptsc_counter(const char* name) {
+  auto it = g_counters.find(name);
+  return it == g_counters.end() ? 0.0 : it->second;
 }
 double rsoptsc_phase_ms(const char* name) {
   resolve_phases();
@@ -473,7 +480,7 @@ int rsoptsc_count_clusters(const double* S, int64_t n, double tol, int32_t range
 
 int rsoptsc_set_gemm_backend(int32_t backend) {
   return guarded([&] {
-    RS_REQUIRE(backend == 0 || backend == 1, "gemm backend must be 0 (cublas) or 1 (ozaki)");
+    RS_REQUIRE(backend >= 0 && backend <= 2, "gemm backend must be 0 (cublas), 1 (ozaki, large only) or 2 (ozaki, forced)");
     set_gemm_backend(backend);
   });
 }

@@ -23,8 +23,13 @@ int gemm_backend() {
 }
 void set_gemm_backend(int b) { g_backend = b; }
 
+// backend 1: tcgen05 path where it pays (large contractions); backend 2: wherever it is legal
+// (parity tests at small sizes).  Small problems are dominated by slicing + launch overheads.
 static bool use_ozaki(int64_t M, int64_t N, int64_t K) {
-  return gemm_backend() == 1 && M >= 512 && N >= 512 && K >= 512 && M <= 65535 && N <= 65535;
+  const int b = gemm_backend();
+  if (b == 0 || M > 65535 || N > 65535) return false;
+  const int64_t lim = b == 2 ? 256 : 1536;
+  return M >= lim && N >= lim && K >= lim;
 }
 
 void gram_AtA(const double* A, int64_t rows, int64_t cols, double* G) {

@@ -81,6 +81,19 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t d
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same MMA with the descriptors given as (lo, hi) words: hi is constant for the whole kernel and lo
+// advances by a compile-time offset per slice, so the single issuing thread spends ~6
+// instructions per MMA (the tensor pipe needs a new M128 N128 K32 MMA every 64 cycles).
+__device__ __forceinline__ void umma_i8_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -123,6 +136,28 @@ __device__ __forceinline__ void pass_groups(int S, int pass, int& p_lo, int& p_h
 // k-blocks per int32 accumulation unit: npairs * K * 127^2 < 2^31
 __device__ __host__ __forceinline__ int max_kblocks(int S) { return (133000 / S) / BK; }
 
+// All MMAs of one k-block of one pass, fully unrolled (S and PASS are compile-time): group p
+// accumulates the pairs (t, p - t) into TMEM columns [(p - p_lo) * BN, +BN).
+template <int S, int PASS>
+__device__ __forceinline__ void issue_stage(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                            uint32_t acc_first) {
+  constexpr int P_LO = PASS == 0 ? S / 2 + 2 : 2;
+  constexpr int P_HI = PASS == 0 ? S + 1 : S / 2 + 1;
+  constexpr uint32_t STEP = SLICE_TILE >> 4;  // descriptor address units (16 B)
+#pragma unroll
+  for (int p = P_LO; p <= P_HI; ++p) {
+    const uint32_t d = tmem_base + (uint32_t)(p - P_LO) * BN;
+#pragma unroll
+    for (int tt = 1; tt < p; ++tt) {
+      const int uu = p - tt;
+      if (tt > S || uu > S) continue;
+      umma_i8_lohi(d, a_lo + (uint32_t)(tt - 1) * STEP, b_lo + (uint32_t)(uu - 1) * STEP, hi, idesc,
+                   tt == 1 ? acc_first : 1u);
+    }
+  }
+}
+
+template <int S>
 __global__ void __launch_bounds__(THREADS, 1)
 k_ozaki_gemm(const __grid_constant__ CUtensorMap tmA_full, const __grid_constant__ CUtensorMap tmA_half,
              const __grid_constant__ CUtensorMap tmB_full, const __grid_constant__ CUtensorMap tmB_half, Params P) {
@@ -139,7 +174,6 @@ k_ozaki_gemm(const __grid_constant__ CUtensorMap tmA_full, const __grid_constant
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = P.S;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full, 1);
@@ -186,6 +220,8 @@ k_ozaki_gemm(const __grid_constant__ CUtensorMap tmA_full, const __grid_constant
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc();
+      // descriptor high word: SBO = 256 B (8 rows x 32 B), version 1, SWIZZLE_32B (see smem_desc_sw32)
+      const uint32_t desc_hi = (256u >> 4) | (1u << 14) | (6u << 29);
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int ti = blockIdx.x; ti < P.num_tiles; ti += gridDim.x) {
@@ -199,16 +235,11 @@ k_ozaki_gemm(const __grid_constant__ CUtensorMap tmA_full, const __grid_constant
             for (int kb = kb0; kb < kb1; ++kb) {
               mbar_wait(full_bar(stage), phase);
               tc_fence_after();
-              const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + OPER_BYTES;
-              for (int p = p_lo; p <= p_hi; ++p) {
-                const uint32_t d = tmem_base + (uint32_t)(p - p_lo) * BN;
-                for (int tt = 1; tt < p; ++tt) {
-                  const int uu = p - tt;
-                  if (tt > S || uu > S) continue;
-                  umma_i8(d, smem_desc_sw32(sa + (tt - 1) * SLICE_TILE), smem_desc_sw32(sb + (uu - 1) * SLICE_TILE), idesc,
-                          (kb > kb0 || tt > 1) ? 1u : 0u);
-                }
-              }
+              const uint32_t sa = base + stage * STAGE_BYTES;
+              const uint32_t a_lo = (sa & 0x3FFFF) >> 4, b_lo = ((sa + OPER_BYTES) & 0x3FFFF) >> 4;
+              const uint32_t acc_first = kb > kb0 ? 1u : 0u;
+              if (pass == 0) issue_stage<S, 0>(tmem_base, a_lo, b_lo, desc_hi, idesc, acc_first);
+              else           issue_stage<S, 1>(tmem_base, a_lo, b_lo, desc_hi, idesc, acc_first);
               umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -406,10 +437,16 @@ static void run(const Operand& a, const Operand& b, double* C, int64_t M, int64_
                 bool accumulate) {
   RS_REQUIRE(a.Kp == b.Kp && a.S == b.S, "ozaki: operand mismatch");
   const int tm = (int)cdiv(M, BM), tn = (int)cdiv(N, BN);
+  // Rasterise in G x G super-blocks: the ~148 tiles in flight then share G panels of A rows and G
+  // panels of B rows and advance through k together, so each panel is fetched from HBM once per
+  // super-block and served from L2 to the other CTAs.
+  const int G = 12;
   std::vector<int2> tiles;
-  for (int j = 0; j < tn; ++j)
-    for (int i = 0; i < tm; ++i)
-      if (!lower_only || (int64_t)j * BN <= (int64_t)i * BM + BM - 1) tiles.push_back(make_int2(i, j));
+  for (int j0 = 0; j0 < tn; j0 += G)
+    for (int i0 = 0; i0 < tm; i0 += G)
+      for (int j = j0; j < std::min(tn, j0 + G); ++j)
+        for (int i = i0; i < std::min(tm, i0 + G); ++i)
+          if (!lower_only || (int64_t)j * BN <= (int64_t)i * BM + BM - 1) tiles.push_back(make_int2(i, j));
   DevBuf<int2> d_tiles(tiles.size());
   RS_CUDA(cudaMemcpyAsync(d_tiles.p, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, ctx().stream));
   Params P;
@@ -418,11 +455,23 @@ static void run(const Operand& a, const Operand& b, double* C, int64_t M, int64_
   const CUtensorMap mAf = make_map(a, a.S), mAh = make_map(a, a.S / 2), mBf = make_map(b, b.S), mBh = make_map(b, b.S / 2);
   static bool attr_set = false;
   if (!attr_set) {
-    RS_CUDA(cudaFuncSetAttribute(k_ozaki_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    RS_CUDA(cudaFuncSetAttribute(k_ozaki_gemm<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    RS_CUDA(cudaFuncSetAttribute(k_ozaki_gemm<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    RS_CUDA(cudaFuncSetAttribute(k_ozaki_gemm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   const int grid = std::min<int>((int)tiles.size(), ctx().sm_count);
-  k_ozaki_gemm<<<grid, THREADS, SMEM_BYTES, ctx().stream>>>(mAf, mAh, mBf, mBh, P);
+  {  // work accounting for bench.py's roofline (algorithmic: unpadded K, computed tiles)
+    const double macs = (double)tiles.size() * BM * BN * (double)a.K;
+    add_counter("ozaki_fp64_flops", 2.0 * macs);
+    add_counter("ozaki_int8_ops", 2.0 * macs * (a.S * (a.S + 1) / 2));
+  }
+  Phase ph("ozaki_gemm");
+  switch (a.S) {
+    case 4: k_ozaki_gemm<4><<<grid, THREADS, SMEM_BYTES, ctx().stream>>>(mAf, mAh, mBf, mBh, P); break;
+    case 6: k_ozaki_gemm<6><<<grid, THREADS, SMEM_BYTES, ctx().stream>>>(mAf, mAh, mBf, mBh, P); break;
+    default: k_ozaki_gemm<8><<<grid, THREADS, SMEM_BYTES, ctx().stream>>>(mAf, mAh, mBf, mBh, P); break;
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   RS_KERNEL_CHECK();
   RS_CUDA(cudaStreamSynchronize(ctx().stream));  // d_tiles and the operands are released by the callers

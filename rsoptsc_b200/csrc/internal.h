@@ -9,6 +9,7 @@ namespace rs {
 
 // ---- launch accounting + phase timers (capi.cu) ------------------------------------
 extern std::atomic<int64_t> g_launches;
+void add_counter(const char* name, double v);  // work counters read back by rsoptsc_counter()
 struct Phase {  // RAII: device time of a region on the library stream
   int id;
   cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -53,13 +53,13 @@ if __name__ == '__main__':
     if mode == 'check':
         for op in (0, 1, 2, 3):
             for (M, N, K) in [(512, 512, 512), (640, 768, 1000), (1300, 900, 2100)]:
-                e1, _ = run(op, M, N, K, 1)
+                e1, _ = run(op, M, N, K, 2)
                 e0, _ = run(op, M, N, K, 0)
                 print('op', op, (M, N, K), 'ozaki max err/(|A||B|) %.2e   cublas %.2e' % (e1, e0), flush=True)
     elif mode == 'chunk':
         # K beyond one int32 accumulation unit (16608) exercises the K-chunk loop
         for op, (M, N, K) in [(3, (1024, 768, 20000)), (0, (1024, 1024, 40000)), (2, (600, 1100, 17000))]:
-            e1, t1 = run(op, M, N, K, 1, scale=False)
+            e1, t1 = run(op, M, N, K, 2, scale=False)
             e0, t0 = run(op, M, N, K, 0, scale=False)
             print('op', op, (M, N, K), 'ozaki err %.2e (%.2f ms)  cublas err %.2e (%.2f ms)' % (e1, t1, e0, t0), flush=True)
     else:

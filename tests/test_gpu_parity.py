@@ -249,7 +249,7 @@ def test_ozaki_gemm_matches_fp64():
             B = np.asfortranarray(rng.normal(size=(K, N)) * sb[None, :])
         Nn = M if op == 0 else N
         out = np.zeros((M, Nn), order="F")
-        _lib.check(lib.rsoptsc_debug_gemm(op, dp(A), dp(B), dp(out), M, Nn, K, 1, 1, None))
+        _lib.check(lib.rsoptsc_debug_gemm(op, dp(A), dp(B), dp(out), M, Nn, K, 2, 1, None))
         ref = {0: lambda: A.T @ A, 1: lambda: A @ B, 2: lambda: A @ B.T, 3: lambda: A.T @ B}[op]()
         aa, bb = np.abs(A), np.abs(B)
         bound = {0: lambda: aa.T @ aa, 1: lambda: aa @ bb, 2: lambda: aa @ bb.T, 3: lambda: aa.T @ bb}[op]()
@@ -259,10 +259,10 @@ def test_ozaki_gemm_matches_fp64():
         assert err.max() < 1e-13, (op, err.max())
 
 
-@pytest.mark.parametrize("backend", [0, 1])
+@pytest.mark.parametrize("backend", [0, 2])
 def test_computeM_with_both_gemm_backends(backend):
-    """n >= 512 so the SVT contractions take the tcgen05 split-integer path (backend 1) or cuBLAS
-    FP64 (backend 0); both must reproduce the oracle."""
+    """The SVT contractions through the tcgen05 split-integer path (backend 2 forces it at this
+    size) or cuBLAS FP64 (backend 0); both must reproduce the oracle."""
     from rsoptsc_b200 import _lib
     lib = _lib.init()
     p = small_problem(300, 700, seed=21)
