@@ -206,6 +206,8 @@ def main():
     launches = api.kernel_launches() - launches0
     t_dev = api.phase_ms("step") / 1e3
     phases = api.phase_report()
+    oz_flops = _lib.load().rsoptsc_counter(b"ozaki_fp64_flops")
+    oz_iops = _lib.load().rsoptsc_counter(b"ozaki_int8_ops")
     api.timers(False)
 
     # end to end through the host-buffer C ABI, pinned host input/output
@@ -262,11 +264,9 @@ def main():
             bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
             bf16_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks.get("bf16_tflops_sustained") else \
                 "fallback (B200_PROFILING.md)"
-            lib = _lib.load()
-            flops = lib.rsoptsc_counter(b"ozaki_fp64_flops")
-            iops = lib.rsoptsc_counter(b"ozaki_int8_ops")
+            flops, iops = oz_flops, oz_iops
             secs = oz["ms"] / 1e3
-            pairs = iops / max(flops, 1.0)
+            pairs = max(iops / max(flops, 1.0), 1.0)
             roof = {"kernel": "k_ozaki_gemm<8> (tcgen05.mma kind::i8, FP64-equivalent)", "bound": "tensor",
                     "achieved": flops / secs / 1e12, "peak": 2.0 * bf16 / pairs, "unit": "TFLOP/s",
                     "frac": (flops / secs / 1e12) / (2.0 * bf16 / pairs), "traffic": None,

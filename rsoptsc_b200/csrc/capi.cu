@@ -12,6 +12,7 @@ namespace rs {
 std::atomic<int64_t> g_launches{0};
 static Context g_ctx;
 static thread_local std::string g_err;
+void release_dense_scratch();  // dense.cu
 
 void ensure_init(int dev);
 Context& ctx() {
@@ -26,7 +27,9 @@ void ensure_init(int dev) {
   if (e != cudaSuccess || count == 0)
     fail(6, __FILE__, __LINE__, std::string("no CUDA device available: the rsoptsc_b200 path has no CPU fallback (") +
                                     cudaGetErrorString(e) + ")");
-  if (g_ctx.initialized) {
+  if (g_ctx.initialized) {  // switching device: cached blocks belong to the old one
+    release_dense_scratch();
+    pool_trim();
     cublasDestroy(g_ctx.cublas); cusolverDnDestroy(g_ctx.cusolver); cudaStreamDestroy(g_ctx.stream);
     g_ctx = Context();
   }
@@ -43,6 +46,48 @@ void ensure_init(int dev) {
   RS_CUDA(cudaGetDeviceProperties(&prop, dev));
   g_ctx.sm_count = prop.multiProcessorCount;
   g_ctx.initialized = true;
+}
+
+// ---- caching device allocator ---------------------------------------------------------
+// Buckets keep 3 significant bits of the size (<= 12.5 % slack).  All library work is issued on
+// one stream, so a recycled buffer is only touched after the kernels that last used it.
+static std::map<size_t, std::vector<void*>>& pool() {  // leaked on purpose: static DevBufs may release at exit
+  static auto* p = new std::map<size_t, std::vector<void*>>();
+  return *p;
+}
+#define g_pool pool()
+static size_t bucket_of(size_t bytes) {
+  if (bytes <= 512) return 512;
+  int hb = 63 - __builtin_clzll((unsigned long long)bytes);
+  const size_t step = (size_t)1 << (hb - 3);
+  return (bytes + step - 1) / step * step;
+}
+void* pool_alloc(size_t bytes) {
+  const size_t b = bucket_of(bytes);
+  auto it = g_pool.find(b);
+  if (it != g_pool.end() && !it->second.empty()) {
+    void* p = it->second.back();
+    it->second.pop_back();
+    return p;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, b);
+  if (e != cudaSuccess) {  // out of memory: give the cached blocks back and retry once
+    cudaGetLastError();
+    pool_trim();
+    e = cudaMalloc(&p, b);
+  }
+  if (e != cudaSuccess)
+    fail(2, __FILE__, __LINE__, std::string("CUDA: cudaMalloc of ") + std::to_string(b) + " bytes failed: " + cudaGetErrorString(e));
+  return p;
+}
+void pool_free(void* p, size_t bytes) {
+  if (p) g_pool[bucket_of(bytes)].push_back(p);
+}
+void pool_trim() {
+  for (auto& kv : g_pool)
+    for (void* p : kv.second) cudaFree(p);
+  g_pool.clear();
 }
 
 // ---- phase timers ---------------------------------------------------------------------
@@ -120,6 +165,7 @@ int rsoptsc_finalize(void) {
     if (!g_ctx.initialized) return;
     resolve_phases();
     release_dense_scratch();
+    pool_trim();
     cublasDestroy(g_ctx.cublas); cusolverDnDestroy(g_ctx.cusolver); cudaStreamDestroy(g_ctx.stream);
     g_ctx = Context();
   });

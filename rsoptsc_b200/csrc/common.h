@@ -50,6 +50,13 @@ struct Error : std::runtime_error {
   } while (0)
 #define RS_KERNEL_CHECK() RS_CUDA(cudaGetLastError())
 
+// Size-bucketed caching allocator (capi.cu): cudaMalloc/cudaFree of the 0.1-1 GB temporaries of
+// every SVT / Lanczos call cost tens of ms and synchronise the device; buffers are recycled
+// instead and only returned to the driver by rsoptsc_finalize() / pool_trim().
+void* pool_alloc(size_t bytes);
+void pool_free(void* p, size_t bytes);
+void pool_trim();
+
 // Owning device allocation (library owns device memory; callers own host buffers).
 template <class T>
 struct DevBuf {
@@ -68,10 +75,10 @@ struct DevBuf {
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) RS_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    if (count) p = static_cast<T*>(pool_alloc(count * sizeof(T)));
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) pool_free(p, n * sizeof(T));
     p = nullptr; n = 0;
   }
   void zero(cudaStream_t s) { if (n) RS_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }

@@ -326,9 +326,10 @@ __global__ void k_rowmax_contig(const double* __restrict__ X, int64_t ld, int R,
   }
 }
 __global__ void k_rowmax_strided(const double* __restrict__ X, int64_t ld, int R, int K, int* __restrict__ ex) {
-  const int r = blockIdx.x * 256 + threadIdx.x;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   double mx = 0;
+#pragma unroll 8
   for (int k = 0; k < K; ++k) mx = fmax(mx, fabs(X[(int64_t)r + (int64_t)k * ld]));
   int e = 0;
   if (mx > 0 && isfinite(mx)) frexp(mx, &e);
@@ -348,11 +349,13 @@ __device__ __forceinline__ void slice_value(double x, int e, int S, int8_t* out)
 }
 __global__ void k_slice_contig(const double* __restrict__ X, int64_t ld, int R, int K, const int* __restrict__ ex, int S,
                                int64_t Rp, int64_t Kp, int8_t* __restrict__ Q) {
-  const int r = blockIdx.y;
+  const int r = blockIdx.y;             // grid covers the padded Rp x Kp extent: pads are zero-filled
   const int k = blockIdx.x * 256 + threadIdx.x;
-  if (k >= K) return;
+  if (k >= Kp) return;
   int8_t q[MAXS];
-  slice_value(X[(int64_t)k + (int64_t)r * ld], ex[r], S, q);
+#pragma unroll
+  for (int t = 0; t < MAXS; ++t) q[t] = 0;
+  if (r < R && k < K) slice_value(X[(int64_t)k + (int64_t)r * ld], ex[r], S, q);
   for (int t = 0; t < S; ++t) Q[((int64_t)t * Rp + r) * Kp + k] = q[t];
 }
 // 32 rows x 32 k per block through shared memory so that both the FP64 reads (along r) and the
@@ -372,7 +375,7 @@ __global__ void k_slice_strided(const double* __restrict__ X, int64_t ld, int R,
   __syncthreads();
   for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
     const int r = r0 + rr, k = k0 + threadIdx.x;
-    if (r < R && k < K)
+    if (r < Rp && k < Kp)  // the grid covers the padded extent; out-of-range entries were sliced as 0
       for (int t = 0; t < S; ++t) Q[((int64_t)t * Rp + r) * Kp + k] = tile[t][rr][threadIdx.x];
   }
 }
@@ -391,17 +394,16 @@ static void slice_operand(const double* X, int64_t ld, int64_t R, int64_t K, boo
   op.Kp = (op.Kp + 127) / 128 * 128;  // keep rows 128-byte aligned for TMA strides
   op.Q.alloc((size_t)S * op.Rp * op.Kp);
   op.ex.alloc(op.Rp);
-  RS_CUDA(cudaMemsetAsync(op.Q.p, 0, op.Q.n, ctx().stream));
+  Phase ph("ozaki_slice");
   RS_CUDA(cudaMemsetAsync(op.ex.p, 0, sizeof(int) * op.Rp, ctx().stream));
+  RS_REQUIRE(op.Rp <= 65535, "ozaki: operand has too many rows for this launch shape");
   if (contig) {
     RS_LAUNCH(k_rowmax_contig, (unsigned)R, 256, 0, X, ld, (int)R, (int)K, op.ex.p);
-    dim3 grid((unsigned)cdiv(K, 256), (unsigned)R);
-    RS_REQUIRE(R <= 65535, "ozaki: operand has too many rows for this launch shape");
+    dim3 grid((unsigned)cdiv(op.Kp, 256), (unsigned)op.Rp);
     RS_LAUNCH(k_slice_contig, grid, 256, 0, X, ld, (int)R, (int)K, op.ex.p, S, op.Rp, op.Kp, op.Q.p);
   } else {
-    RS_LAUNCH(k_rowmax_strided, (unsigned)cdiv(R, 256), 256, 0, X, ld, (int)R, (int)K, op.ex.p);
-    dim3 grid((unsigned)cdiv(K, 32), (unsigned)cdiv(R, 32)), block(32, 8);
-    RS_REQUIRE(cdiv(R, 32) <= 65535, "ozaki: operand has too many rows for this launch shape");
+    RS_LAUNCH(k_rowmax_strided, (unsigned)cdiv(R, 64), 64, 0, X, ld, (int)R, (int)K, op.ex.p);
+    dim3 grid((unsigned)cdiv(op.Kp, 32), (unsigned)cdiv(op.Rp, 32)), block(32, 8);
     RS_LAUNCH(k_slice_strided, grid, block, 0, X, ld, (int)R, (int)K, op.ex.p, S, op.Rp, op.Kp, op.Q.p);
   }
 }
@@ -474,7 +476,8 @@ static void run(const Operand& a, const Operand& b, double* C, int64_t M, int64_
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   RS_KERNEL_CHECK();
-  RS_CUDA(cudaStreamSynchronize(ctx().stream));  // d_tiles and the operands are released by the callers
+  // d_tiles and the operand slices go back to the caching allocator when the callers return; the
+  // single library stream orders any reuse after this kernel.
 }
 
 }  // namespace oz
