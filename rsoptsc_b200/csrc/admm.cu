@@ -128,7 +128,10 @@ void run_admm(const double* d_X, int64_t m, int64_t n, const Support& s, double 
     }
     // step 1: J = SVT_{1/mu}(Z - Y3/mu)                      R :142-155
     const double a_f2 = build_A(s, st.Zs.p, Y3.p, mu, A.p);
-    const bool j_zero = std::sqrt(a_f2) <= tau;
+    // J == 0 exactly when sigma_1(A) <= tau.  ||A||_F/sqrt(n) <= sigma_1 <= ||A||_F settles most
+    // iterations; in between, a residual-certified Lanczos value of sigma_1 (1e-10 relative) decides.
+    bool j_zero = std::sqrt(a_f2) <= tau;
+    if (!j_zero && std::sqrt(a_f2 / (double)n) <= tau) j_zero = spectral_norm(A.p, n, n) <= tau * (1.0 - 1e-8);
     if (!j_zero) { svt_inplace(svt, A.p, n, tau); ++res.n_svt; }
     const double* J = j_zero ? nullptr : A.p;
     gather_support_term(s, st.Zs.p, J, Y3.p, mu, st.q.p);    // (Z - J + Y3/mu) on the support
