@@ -130,22 +130,36 @@ __global__ void k_scatter_add(const int* __restrict__ rowof, const int* __restri
   if (p < nnz) a[(int64_t)rowof[p] + (int64_t)col[p] * n] += scale * zs[p];
 }
 
-double build_A(const Support& s, const double* d_Zs, const double* d_Y3, double mu, double* d_A) {
+// entry p of the support lives at block-storage offset off[p] (Support::dense_off)
+__global__ void k_scatter_add_off(const long long* __restrict__ off, const double* __restrict__ zs, int64_t nnz,
+                                  double scale, double* __restrict__ a) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nnz) a[off[p]] += scale * zs[p];
+}
+
+// A = Z - Y3/mu on the block-diagonal storage; fro2[c] = ||A_c||_F^2 per connected component
+void build_A(const Support& s, const double* d_Zs, const double* d_Y3, double mu, double* d_A,
+             std::vector<double>& fro2) {
   Phase ph("build_A");
-  const int64_t nn = s.n * s.n;
+  const int64_t nn = s.total_dense;
   RS_LAUNCH(k_scale_neg, RED_BLOCKS * 2, 256, 0, d_Y3, mu, nn, d_A);
-  if (s.nnz) RS_LAUNCH(k_scatter_add, cdiv(s.nnz, 256), 256, 0, s.rowof.p, s.col.p, d_Zs, s.nnz, s.n, 1.0, d_A);
-  RS_LAUNCH(k_frob2, RED_BLOCKS, RED_THREADS, 0, d_A, nn, red().partial.p);
-  return finish_sum(RED_BLOCKS);
+  if (s.nnz) RS_LAUNCH(k_scatter_add_off, cdiv(s.nnz, 256), 256, 0, s.dense_off.p, d_Zs, s.nnz, 1.0, d_A);
+  fro2.resize(s.comp_n.size());
+  for (size_t c = 0; c < s.comp_n.size(); ++c) {
+    const int64_t cnt = s.comp_n[c] * s.comp_n[c];
+    const int blocks = (int)std::min<int64_t>(RED_BLOCKS, std::max<int64_t>(1, cnt / 4096));
+    RS_LAUNCH(k_frob2, blocks, RED_THREADS, 0, d_A + s.comp_off[c], cnt, red().partial.p);
+    fro2[c] = finish_sum(blocks);
+  }
 }
 
 // ---- q[p] = Zs - J + Y3/mu on the support -------------------------------------------
-__global__ void k_gather_term(const int* __restrict__ rowof, const int* __restrict__ col, const double* __restrict__ zs,
+__global__ void k_gather_term(const long long* __restrict__ doff, const double* __restrict__ zs,
                               const double* __restrict__ J, const double* __restrict__ y3, double mu, int64_t nnz,
-                              int64_t n, double* __restrict__ q) {
+                              double* __restrict__ q) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nnz) return;
-  const int64_t off = (int64_t)rowof[p] + (int64_t)col[p] * n;
+  const int64_t off = doff[p];
   const double j = J ? J[off] : 0.0;
   q[p] = zs[p] - j + y3[off] / mu;
 }
@@ -153,7 +167,7 @@ void gather_support_term(const Support& s, const double* d_Zs, const double* d_J
                          double* d_q) {
   Phase ph("gather");
   if (s.nnz)
-    RS_LAUNCH(k_gather_term, cdiv(s.nnz, 256), 256, 0, s.rowof.p, s.col.p, d_Zs, d_J, d_Y3, mu, s.nnz, s.n, d_q);
+    RS_LAUNCH(k_gather_term, cdiv(s.nnz, 256), 256, 0, s.dense_off.p, d_Zs, d_J, d_Y3, mu, s.nnz, d_q);
 }
 
 // ---- Y3 += mu (Z - J) ------------------------------------------------------------------
@@ -179,14 +193,14 @@ __global__ void k_y3_sub_J(const double* __restrict__ J, double mu, int64_t coun
   if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 // sparse part: Y3[i,j] += mu*Zs ; partial sums of (Zs-J)^2 - J^2 over the support
-__global__ void k_y3_add_Z(const int* __restrict__ rowof, const int* __restrict__ col, const double* __restrict__ zs,
-                           const double* __restrict__ J, double mu, int64_t nnz, int64_t n, double* __restrict__ y3,
+__global__ void k_y3_add_Z(const long long* __restrict__ doff, const double* __restrict__ zs,
+                           const double* __restrict__ J, double mu, int64_t nnz, double* __restrict__ y3,
                            double* __restrict__ partial) {
   __shared__ double sm[RED_THREADS / 32 + 1];
   double acc = 0;
   const int64_t stride = (int64_t)gridDim.x * RED_THREADS;
   for (int64_t p = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x; p < nnz; p += stride) {
-    const int64_t off = (int64_t)rowof[p] + (int64_t)col[p] * n;
+    const int64_t off = doff[p];
     const double z = zs[p];
     const double j = J ? J[off] : 0.0;
     y3[off] += mu * z;
@@ -198,7 +212,7 @@ __global__ void k_y3_add_Z(const int* __restrict__ rowof, const int* __restrict_
 
 double update_Y3(const Support& s, const double* d_Zs, const double* d_J, double mu, double* d_Y3) {
   Phase ph("update_Y3");
-  const int64_t nn = s.n * s.n;
+  const int64_t nn = s.total_dense;  // block-diagonal storage (sum n_c^2)
   double total = 0;
   // order matters: the sparse kernel reads J on the support, so it may run after the dense one
   if (d_J) {
@@ -206,7 +220,7 @@ double update_Y3(const Support& s, const double* d_Zs, const double* d_J, double
     total += finish_sum(RED_BLOCKS);
   }
   const int blocks = 148;
-  RS_LAUNCH(k_y3_add_Z, blocks, RED_THREADS, 0, s.rowof.p, s.col.p, d_Zs, d_J, mu, s.nnz, s.n, d_Y3, red().partial.p);
+  RS_LAUNCH(k_y3_add_Z, blocks, RED_THREADS, 0, s.dense_off.p, d_Zs, d_J, mu, s.nnz, d_Y3, red().partial.p);
   total += finish_sum(blocks);
   return total > 0 ? total : 0.0;
 }
@@ -269,6 +283,10 @@ void threshold_symmetrise_sparse(const Support& s, const double* d_Zs, double* d
   Phase ph("symm");
   RS_CUDA(cudaMemsetAsync(d_W, 0, sizeof(double) * s.n * s.n, ctx().stream));
   if (s.nnz) RS_LAUNCH(k_symmetrise_sparse, cdiv(s.nnz, 256), 256, 0, s.rowof.p, s.col.p, d_Zs, s.nnz, s.n, d_W);
+}
+void scatter_support_blocks(const Support& s, const double* d_Zs, double* d_Zb) {
+  RS_CUDA(cudaMemsetAsync(d_Zb, 0, sizeof(double) * s.total_dense, ctx().stream));
+  if (s.nnz) RS_LAUNCH(k_scatter_add_off, cdiv(s.nnz, 256), 256, 0, s.dense_off.p, d_Zs, s.nnz, 1.0, d_Zb);
 }
 void scatter_support_dense(const Support& s, const double* d_Zs, double* d_Z) {
   Phase ph("symm");

@@ -33,14 +33,22 @@ struct Support {
                                        //      rowidx[q] = i, csrpos[q] = p
   std::vector<int> h_rowptr, h_col;
   int max_col_nnz = 0;
+  // Connected components of the support graph.  Z, Y3, A = Z - Y3/mu and J = SVT(A) are block
+  // diagonal over them (exactly: the SVD of a block-diagonal matrix is block diagonal), so the
+  // dense n x n state is stored as the concatenation of the n_c x n_c diagonal blocks and the SVT
+  // runs per block (cost sum n_c^3 instead of n^3).
+  std::vector<int64_t> comp_n, comp_off;  // block sizes / offsets (in doubles) into the dense state
+  int64_t total_dense = 0;                // sum n_c^2
+  DevBuf<long long> dense_off;            // per support entry: offset of (i,j) inside the block storage
 };
 void build_support_from_idx(Support& s, const int32_t* h_idx, int64_t n, int K);
 void build_support_from_dense_mask(Support& s, const double* h_D, int64_t n);
 
 // ---- dense elementwise (dense.cu) ---------------------------------------------------
 void normalize_columns(const double* d_data, int64_t m, int64_t n, double* d_X);
-// A = -Y3/mu (+ Z scattered on the support); returns ||A||_F^2
-double build_A(const Support& s, const double* d_Zs, const double* d_Y3, double mu, double* d_A);
+// A = -Y3/mu (+ Z scattered on the support) in block-diagonal storage; fro2[c] = ||A_c||_F^2
+void build_A(const Support& s, const double* d_Zs, const double* d_Y3, double mu, double* d_A,
+             std::vector<double>& fro2);
 // q[p] = Zs[p] - J[i,j] + Y3[i,j]/mu on the support (J may be null == 0)
 void gather_support_term(const Support& s, const double* d_Zs, const double* d_J, const double* d_Y3,
                          double mu, double* d_q);
@@ -50,6 +58,7 @@ void scale_columns(double* d_T, int64_t rows, int64_t cols, const double* d_scal
 void threshold_symmetrise_dense(const double* d_Z, int64_t n, double* d_W);
 void threshold_symmetrise_sparse(const Support& s, const double* d_Zs, double* d_W /* n x n, zeroed here */);
 void scatter_support_dense(const Support& s, const double* d_Zs, double* d_Z /* n x n, zeroed here */);
+void scatter_support_blocks(const Support& s, const double* d_Zs, double* d_Zb /* block storage, zeroed here */);
 double frob2(const double* d_a, int64_t count);
 
 // ---- column-local ADMM step (admm_kernels.cu) ---------------------------------------

@@ -68,6 +68,33 @@ def test_computeM_matches_oracle(m, n, lam):
     assert np.count_nonzero(got["Z"][O.mask_from_idx(p["idx"], n)]) == 0
 
 
+def test_computeM_disconnected_support_matches_oracle():
+    """kNN graph with several connected components (the library then runs one SVT per component on a
+    block-diagonal dense state); the oracle works on the full n x n matrices."""
+    from rsoptsc_b200.synthetic import synthetic_lognorm
+    n, m, K = 420, 150, 10
+    data, _ = synthetic_lognorm(m, n, seed=4)
+    X = O.normalize_columns(data)
+    rng = np.random.default_rng(4)
+    sizes = [200, 150, 60, 9, 1]                      # includes a singleton component
+    emb = np.concatenate([rng.normal(size=(s, 3)) + 1000.0 * g for g, s in enumerate(sizes)])
+    perm = rng.permutation(n)                         # components interleaved in cell order
+    emb = emb[perm]
+    idx = np.empty((n, K), dtype=np.int32)
+    d2 = ((emb[:, None, :] - emb[None, :, :]) ** 2).sum(-1)
+    group = np.repeat(np.arange(len(sizes)), sizes)[perm]
+    for i in range(n):
+        same = np.flatnonzero(group == group[i])
+        order = same[np.argsort(d2[i, same], kind="stable")]
+        take = order[:K]
+        idx[i] = np.resize(take, K)                   # small components: repeated (duplicate) neighbours
+    ref = O.computeM(O.mask_from_idx(idx, n), X, 0.5, literal=False)
+    got = api.computeM(None, X, 0.5, idx=idx)
+    assert got["iters"] == ref["iters"]
+    assert relF(got["Z"], ref["Z"]) < 1e-6
+    assert abs(got["E"] - ref["E"]) < 1e-8 * ref["E"]
+
+
 def test_computeM_dense_mask_signature():
     p = small_problem(100, 120, seed=5)
     n = 120
