@@ -5,6 +5,7 @@
 
 #include "internal.h"
 #include "lanczos.h"
+#include "sparse.h"
 
 namespace rs {
 
@@ -30,36 +31,166 @@ __global__ void k_laplacian(const double* __restrict__ S, const double* __restri
   }
 }
 
-static void laplacian_spectrum(const double* d_S, int64_t n, std::vector<double>& vals) {
+// diagonal block of the Laplacian over the cells `members` (ascending): Lc[a,b] = delta - (dd_i S_ij) dd_j
+__global__ void k_laplacian_block(const double* __restrict__ S, const double* __restrict__ dd, int64_t n,
+                                  const int* __restrict__ members, int64_t nc, double* __restrict__ Lc) {
+  const int64_t b = blockIdx.y;
+  const int64_t j = members[b];
+  const double dj = dd[j];
+  for (int64_t a = (int64_t)blockIdx.x * ET + threadIdx.x; a < nc; a += (int64_t)gridDim.x * ET) {
+    const int64_t i = members[a];
+    const double v = (dd[i] * S[i + j * n]) * dj;
+    Lc[a + b * nc] = (a == b ? 1.0 : 0.0) - v;
+  }
+}
+
+// All eigenvalues of one dense symmetric block (lower triangle), appended to `out`.
+static void block_eigenvalues(double* d_L, int64_t nc, std::vector<double>& out) {
+  Context& c = ctx();
+  DevBuf<double> lam(nc);
+  int lwork = 0;
+  RS_CUSOLVER(cusolverDnDsyevd_bufferSize(c.cusolver, CUSOLVER_EIG_MODE_NOVECTOR, CUBLAS_FILL_MODE_LOWER, (int)nc, d_L,
+                                          (int)nc, lam.p, &lwork));
+  DevBuf<double> work((size_t)std::max(lwork, 1));
+  DevBuf<int> info(1);
+  {
+    Phase ph("eig");
+    RS_CUSOLVER(cusolverDnDsyevd(c.cusolver, CUSOLVER_EIG_MODE_NOVECTOR, CUBLAS_FILL_MODE_LOWER, (int)nc, d_L, (int)nc,
+                                 lam.p, work.p, lwork, info.p));
+  }
+  const size_t at = out.size();
+  out.resize(at + nc);
+  int hinfo = 0;
+  RS_CUDA(cudaMemcpyAsync(out.data() + at, lam.p, sizeof(double) * nc, cudaMemcpyDeviceToHost, c.stream));
+  RS_CUDA(cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  RS_CUDA(cudaStreamSynchronize(c.stream));
+  RS_REQUIRE(hinfo == 0, "get_components: eigensolver failed");
+}
+
+// Spectrum of I - D^-1/2 S D^-1/2.  The Laplacian is block diagonal over the connected components
+// of the non-zero pattern of S, so its spectrum is the union of the blocks' spectra (sum n_c^3
+// eigensolver work instead of n^3).  The pattern is taken from the CSC view when S is sparse.
+static void laplacian_spectrum(const double* d_S, int64_t n, std::vector<double>& vals, const Compressed* csc_in = nullptr) {
   Context& c = ctx();
   RS_REQUIRE(n <= 46340, "get_components: n too large for the dense eigensolver");
-  DevBuf<double> ones(n), deg(n), L((size_t)n * n), lam(n);
+  RS_REQUIRE(n <= 65535, "get_components: n too large for this launch shape");
+  DevBuf<double> ones(n), deg(n);
   RS_LAUNCH(k_fill_ones, (unsigned)cdiv(n, ET), ET, 0, ones.p, n);
   DenseMatvec mv;
   mv.init(d_S, n, n);
   mv.mul_n(ones.p, deg.p);                                   // degree = S 1      (R :98)
   RS_LAUNCH(k_inv_sqrt, (unsigned)cdiv(n, ET), ET, 0, deg.p, n);
-  dim3 grid((unsigned)std::min<int64_t>(cdiv(n, ET), 64), (unsigned)std::min<int64_t>(n, 65535));
-  RS_REQUIRE(n <= 65535, "get_components: n too large for this launch shape");
-  RS_LAUNCH(k_laplacian, grid, ET, 0, d_S, deg.p, n, L.p);
-  int lwork = 0;
-  RS_CUSOLVER(cusolverDnDsyevd_bufferSize(c.cusolver, CUSOLVER_EIG_MODE_NOVECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, L.p,
-                                          (int)n, lam.p, &lwork));
-  DevBuf<double> work((size_t)lwork);
-  DevBuf<int> info(1);
-  {
-    Phase ph("eig");
-    RS_CUSOLVER(cusolverDnDsyevd(c.cusolver, CUSOLVER_EIG_MODE_NOVECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, L.p, (int)n,
-                                 lam.p, work.p, lwork, info.p));
+  // connected components of the pattern (host union-find over the sparse entries)
+  Compressed own;
+  const Compressed* csc = csc_in;
+  if (!csc) { compress(d_S, n, false, own); csc = &own; }
+  std::vector<int> comp(n, 0);
+  std::vector<std::vector<int>> members;
+  if (csc->nnz <= 128 * n) {
+    std::vector<int> ptr(n + 1), idx(std::max<int64_t>(csc->nnz, 1)), parent(n);
+    csc->ptr.download(ptr.data(), n + 1, c.stream);
+    if (csc->nnz) csc->idx.download(idx.data(), csc->nnz, c.stream);
+    RS_CUDA(cudaStreamSynchronize(c.stream));
+    for (int64_t i = 0; i < n; ++i) parent[i] = (int)i;
+    auto find = [&](int x) {
+      while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
+      return x;
+    };
+    for (int64_t j = 0; j < n; ++j)
+      for (int e = ptr[j]; e < ptr[j + 1]; ++e) {
+        const int a = find((int)j), b = find(idx[e]);
+        if (a != b) parent[std::max(a, b)] = std::min(a, b);
+      }
+    std::vector<int> id(n, -1);
+    for (int64_t i = 0; i < n; ++i) {
+      const int r = find((int)i);
+      if (id[r] < 0) { id[r] = (int)members.size(); members.emplace_back(); }
+      members[id[r]].push_back((int)i);
+    }
+  } else {  // effectively dense: one block
+    members.emplace_back(n);
+    for (int64_t i = 0; i < n; ++i) members[0][i] = (int)i;
   }
-  vals.resize(n);
-  int hinfo = 0;
-  RS_CUDA(cudaMemcpyAsync(vals.data(), lam.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
-  RS_CUDA(cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-  RS_CUDA(cudaStreamSynchronize(c.stream));
-  RS_REQUIRE(hinfo == 0, "get_components: eigensolver failed");
+  vals.clear();
+  vals.reserve(n);
+  DevBuf<int> d_mem(n);
+  for (const auto& mem : members) {
+    const int64_t nc = (int64_t)mem.size();
+    DevBuf<double> L((size_t)nc * nc);
+    d_mem.upload(mem.data(), nc, c.stream);
+    dim3 grid((unsigned)std::min<int64_t>(cdiv(nc, ET), 64), (unsigned)nc);
+    RS_LAUNCH(k_laplacian_block, grid, ET, 0, d_S, deg.p, n, d_mem.p, nc, L.p);
+    RS_CUDA(cudaStreamSynchronize(c.stream));               // `mem` staging must finish before the next upload
+    block_eigenvalues(L.p, nc, vals);
+  }
   for (auto& v : vals) v = std::fabs(v);                     // abs(Re(.))   (R :102)
   std::sort(vals.begin(), vals.end());                       // sort         (R :104)
+}
+
+// ---- a15 on a sparse similarity: PCA scores by Lanczos ---------------------------------------------
+// prcomp(t(S), center = TRUE)$x[, 1:ncomp] (R/Clustering.R:133).  T = t(S); centring its columns gives
+// Tc = S^T - 1 mu^T with mu = rowMeans(S); the scores are Tc V for the top right singular vectors V of
+// Tc, i.e. the top eigenvectors of Tc^T Tc -- two SpMVs and two rank-one corrections per Lanczos step
+// instead of an n^3 dense PCA of which only ncomp columns are used.
+__global__ void k_dot1(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* __restrict__ out) {
+  __shared__ double sm[1024 / 32 + 1];
+  double acc = 0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) acc += a[i] * b[i];
+  acc = block_sum<1024>(acc, sm);
+  if (threadIdx.x == 0) *out = acc;
+}
+__global__ void k_sub_scalar(double* __restrict__ y, int64_t n, const double* __restrict__ s) {
+  const int64_t i = (int64_t)blockIdx.x * ET + threadIdx.x;
+  if (i < n) y[i] -= *s;
+}
+__global__ void k_sub_scaled(double* __restrict__ w, const double* __restrict__ mu, int64_t n, const double* __restrict__ s) {
+  const int64_t i = (int64_t)blockIdx.x * ET + threadIdx.x;
+  if (i < n) w[i] -= mu[i] * (*s);
+}
+__global__ void k_scale_vec(double* __restrict__ v, int64_t n, double f) {
+  const int64_t i = (int64_t)blockIdx.x * ET + threadIdx.x;
+  if (i < n) v[i] *= f;
+}
+
+static void pca_scores_sparse(const Compressed& csr, const Compressed& csc, int64_t n, int ncomp, double* d_scores) {
+  Phase ph("pca");
+  const unsigned g = (unsigned)cdiv(n, ET);
+  DevBuf<double> ones(n), mu(n), t(n), scal(2);
+  RS_LAUNCH(k_fill_ones, g, ET, 0, ones.p, n);
+  spmv(csr, ones.p, mu.p);
+  RS_LAUNCH(k_scale_vec, g, ET, 0, mu.p, n, 1.0 / (double)n);
+  auto tc_mul = [&](const double* v, double* out) {          // out = Tc v = S^T v - (mu.v) 1
+    spmv(csc, v, out);
+    RS_LAUNCH(k_dot1, 1, 1024, 0, mu.p, v, n, scal.p);
+    RS_LAUNCH(k_sub_scalar, g, ET, 0, out, n, scal.p);
+  };
+  Lanczos lz;
+  const int cap = (int)std::min<int64_t>(n, 1024);
+  lz.init(n, cap, [&](const double* v, double* w) {
+    tc_mul(v, t.p);
+    spmv(csr, t.p, w);                                       // w = Tc^T t = S t - mu sum(t)
+    RS_LAUNCH(k_dot1, 1, 1024, 0, ones.p, t.p, n, scal.p + 1);
+    RS_LAUNCH(k_sub_scaled, g, ET, 0, w, mu.p, n, scal.p + 1);
+  });
+  std::vector<double> theta, S;
+  int next = std::min(cap, std::max(2 * ncomp + 30, 48));
+  while (true) {
+    lz.advance(next - lz.steps);
+    lz.ritz(theta, S, /*last_row_only=*/true);
+    const int st = lz.steps;
+    RS_REQUIRE(st >= ncomp, "count_clusters: similarity matrix has fewer than n_comp non-trivial components");
+    bool conv = true;
+    for (int i = 0; i < ncomp && conv; ++i)
+      conv = std::fabs(lz.beta[st - 1] * S[st - 1 - i]) <= 1e-13 * theta[st - 1];
+    if (conv || lz.exhausted || st >= lz.max_steps) { lz.ritz(theta, S); break; }
+    next = std::min(lz.max_steps, st + std::max(32, st / 3));
+  }
+  std::vector<int> sel(ncomp);
+  for (int i = 0; i < ncomp; ++i) sel[i] = lz.steps - 1 - i;
+  DevBuf<double> V((size_t)n * ncomp);
+  lz.ritz_vectors(S, sel, V.p);
+  for (int i = 0; i < ncomp; ++i) tc_mul(V.p + (size_t)i * n, d_scores + (size_t)i * n);
+  RS_CUDA(cudaStreamSynchronize(ctx().stream));
 }
 
 void get_components(const double* d_S, int64_t n, double tol, double* h_vals, int32_t* n_eigs) {
@@ -145,16 +276,67 @@ __global__ void k_min_update(const double* __restrict__ D, int64_t n, int64_t me
 }
 // nearest / second-nearest medoid distance per object
 __global__ void k_nearest_two(const double* __restrict__ D, int64_t n, const int* __restrict__ med, int k, double s,
-                              double* __restrict__ dysma, double* __restrict__ dysmb) {
+                              double* __restrict__ dysma, double* __restrict__ dysmb, int* __restrict__ near,
+                              int* __restrict__ ties) {
   const int64_t j = (int64_t)blockIdx.x * ET + threadIdx.x;
   if (j >= n) return;
   double a = s, b = s;
+  int na = 0;
   for (int t = 0; t < k; ++t) {
     const double d = D[j + (int64_t)med[t] * n];
-    if (a > d) { b = a; a = d; } else if (b > d) { b = d; }
+    if (a > d) { b = a; a = d; na = t; } else if (b > d) { b = d; }
   }
+  int cnt = 0;  // medoids at exactly the closest distance (pam.c tests dys[ij] == dysma[j])
+  for (int t = 0; t < k; ++t) cnt += D[j + (int64_t)med[t] * n] == a;
   dysma[j] = a;
   dysmb[j] = b;
+  near[j] = na;
+  ties[j] = cnt;
+}
+
+// Single-pass SWAP cost for k <= KMAX: T[h][t] = sum_j C_{j, med[t], h}.  Every object j adds its
+// "not closest" term to all medoids and a correction to the medoid(s) it is closest to.
+template <int KMAX>
+__global__ void k_swap_cost_fast(const double* __restrict__ D, int64_t n, const int* __restrict__ med, int k,
+                                 const int* __restrict__ is_med, const double* __restrict__ dysma,
+                                 const double* __restrict__ dysmb, const int* __restrict__ near,
+                                 const int* __restrict__ ties, double* __restrict__ T) {
+  __shared__ double sm[ET / 32 + 1];
+  const int64_t h = blockIdx.x;
+  if (is_med[h]) {
+    for (int t = threadIdx.x; t < k; t += ET) T[h * k + t] = INFINITY;
+    return;
+  }
+  const double* dh = D + h * n;
+  double shared_term = 0;
+  double corr[KMAX];
+#pragma unroll
+  for (int t = 0; t < KMAX; ++t) corr[t] = 0;
+  for (int64_t j = threadIdx.x; j < n; j += ET) {
+    const double a = dysma[j], b = dysmb[j], d = dh[j];
+    const double base = d < a ? d - a : 0.0;
+    shared_term += base;
+    const double cterm = ((b > d ? d : b) - a) - base;
+    if (ties[j] == 1) {
+      const int nr = near[j];
+#pragma unroll
+      for (int t = 0; t < KMAX; ++t) corr[t] += (t == nr) ? cterm : 0.0;
+    } else {
+      for (int t = 0; t < k; ++t)
+        if (D[j + (int64_t)med[t] * n] == a) {
+#pragma unroll
+          for (int u = 0; u < KMAX; ++u) corr[u] += (u == t) ? cterm : 0.0;
+        }
+    }
+  }
+  shared_term = block_sum<ET>(shared_term, sm);
+#pragma unroll
+  for (int t = 0; t < KMAX; ++t) {
+    if (t < k) {
+      const double v = block_sum<ET>(corr[t], sm);
+      if (threadIdx.x == 0) T[h * k + t] = shared_term + v;
+    }
+  }
 }
 // SWAP cost T[h][t] = sum_j C_{j, med[t], h} for every non-medoid h (one CTA per h)   [KR p.104]
 static constexpr int PAM_KMAX = 64;
@@ -258,7 +440,7 @@ __global__ void k_assign(const double* __restrict__ D, int64_t n, const int* __r
 struct PamEngine {
   int64_t n = 0;
   DevBuf<double> D, dysma, dysmb, gain, T, scal;
-  DevBuf<int> is_med, med;
+  DevBuf<int> is_med, med, near_t, ties;
   DevBuf<long long> lidx;
   DevBuf<int32_t> near;
   double s = 0;
@@ -269,7 +451,7 @@ struct PamEngine {
     cudaStream_t st = ctx().stream;
     RS_REQUIRE(n <= 65535, "pam: more than 65535 observations (cluster::pam has the same limit)");
     D.alloc((size_t)n * n); dysma.alloc(n); dysmb.alloc(n); gain.alloc(n); T.alloc((size_t)n * kmax); scal.alloc(256);
-    is_med.alloc(n); med.alloc(kmax); lidx.alloc(1); near.alloc(n);
+    is_med.alloc(n); med.alloc(kmax); lidx.alloc(1); near.alloc(n); near_t.alloc(n); ties.alloc(n);
     dim3 grid((unsigned)std::min<int64_t>(cdiv(n, ET), 64), (unsigned)n);
     RS_LAUNCH(k_pairwise_dist, grid, ET, 0, d_P, n, dim, D.p);
     RS_LAUNCH(k_max_partial, 148, ET, 0, D.p, n * n, scal.p);
@@ -309,7 +491,7 @@ struct PamEngine {
     for (int m : medoids) flags[m] = 1;
     is_med.upload(flags.data(), n, st);
     med.upload(medoids.data(), k, st);
-    RS_LAUNCH(k_nearest_two, (unsigned)cdiv(n, ET), ET, 0, D.p, n, med.p, k, s, dysma.p, dysmb.p);
+    RS_LAUNCH(k_nearest_two, (unsigned)cdiv(n, ET), ET, 0, D.p, n, med.p, k, s, dysma.p, dysmb.p, near_t.p, ties.p);
     double sky = 0;
     {  // sky = sum dysma
       std::vector<double> h(n);
@@ -318,7 +500,10 @@ struct PamEngine {
       for (double v : h) sky += v;
     }
     for (int guard = 0; guard < 100000 && k < n; ++guard) {
-      RS_LAUNCH(k_swap_cost, (unsigned)n, ET, 0, D.p, n, med.p, k, is_med.p, dysma.p, dysmb.p, T.p);
+      if (k <= 32)
+        RS_LAUNCH(k_swap_cost_fast<32>, (unsigned)n, ET, 0, D.p, n, med.p, k, is_med.p, dysma.p, dysmb.p, near_t.p, ties.p, T.p);
+      else
+        RS_LAUNCH(k_swap_cost, (unsigned)n, ET, 0, D.p, n, med.p, k, is_med.p, dysma.p, dysmb.p, T.p);
       RS_LAUNCH(k_argmin_first, 1, ET, 0, T.p, n * k, scal.p, lidx.p);
       double dz = 0;
       long long where = -1;
@@ -334,7 +519,7 @@ struct PamEngine {
       sky += dz;
       is_med.upload(flags.data(), n, st);
       med.upload(medoids.data(), k, st);
-      RS_LAUNCH(k_nearest_two, (unsigned)cdiv(n, ET), ET, 0, D.p, n, med.p, k, s, dysma.p, dysmb.p);
+      RS_LAUNCH(k_nearest_two, (unsigned)cdiv(n, ET), ET, 0, D.p, n, med.p, k, s, dysma.p, dysmb.p, near_t.p, ties.p);
     }
     RS_LAUNCH(k_assign, (unsigned)cdiv(n, ET), ET, 0, D.p, n, med.p, k, near.p);
     std::vector<int32_t> nr(n);
@@ -369,14 +554,21 @@ void count_clusters(const double* d_S, int64_t n, double tol, int lo, int hi, in
   RS_REQUIRE(lo >= 1 && hi >= lo && hi < n, "count_clusters: invalid range");
   RS_REQUIRE(n_comp >= 1 && n_comp <= n, "count_clusters: invalid n_comp");
   std::vector<double> vals;
-  laplacian_spectrum(d_S, n, vals);                                       // R :63
+  Compressed csr, csc;
+  compress(d_S, n, true, csr);
+  compress(d_S, n, false, csc);
+  laplacian_spectrum(d_S, n, vals, &csc);                                 // R :63
   int solo = 0;
   for (double v : vals) solo += v <= tol;
   const double tau = solo <= 5 ? 0.3 : (solo <= 10 ? 0.4 : 0.5);          // R :64-70
   // GetEnsemble (R :125-154): PCA scores of t(S), PAM for every k in range, consensus
   DevBuf<double> scores((size_t)n * n_comp);
-  std::vector<double> eig;
-  pca_spectrum(d_S, n, n, eig, scores.p, n_comp);                         // R :133
+  if (csr.nnz <= 128 * n) {
+    pca_scores_sparse(csr, csc, n, n_comp, scores.p);                     // R :133 (sparse similarity)
+  } else {
+    std::vector<double> eig;
+    pca_spectrum(d_S, n, n, eig, scores.p, n_comp);                       // R :133 (dense similarity)
+  }
   const int R = hi - lo + 1;
   std::vector<int32_t> table((size_t)R * n);
   {

@@ -13,6 +13,7 @@
 
 #include "internal.h"
 #include "lanczos.h"
+#include "sparse.h"
 
 namespace rs {
 
@@ -20,11 +21,6 @@ static constexpr int NT = 256;
 static constexpr int GP = 64;       // partial blocks for the k x k Grams / column sums
 static constexpr int NMF_KMAX = 128;
 
-struct Compressed {  // CSR (by row) or CSC (by column) of an n x n matrix
-  int64_t n = 0, nnz = 0;
-  DevBuf<int> ptr, idx;
-  DevBuf<double> val;
-};
 
 // ---- dense -> compressed -------------------------------------------------------------------
 __global__ void k_count_cols(const double* __restrict__ V, int64_t n, int* __restrict__ cnt) {
@@ -74,7 +70,7 @@ __global__ void k_fill_rows(const double* __restrict__ V, int64_t n, const int* 
   }
 }
 
-static void compress(const double* d_V, int64_t n, bool by_row, Compressed& out) {
+void compress(const double* d_V, int64_t n, bool by_row, Compressed& out) {
   cudaStream_t s = ctx().stream;
   out.n = n;
   DevBuf<int> cnt(n);
@@ -106,7 +102,7 @@ __global__ void k_spmv(const int* __restrict__ ptr, const int* __restrict__ idx,
   acc = warp_sum(acc);
   if (lane == 0) y[r] = acc;
 }
-static void spmv(const Compressed& A, const double* x, double* y) {
+void spmv(const Compressed& A, const double* x, double* y) {
   RS_LAUNCH(k_spmv, (unsigned)cdiv(A.n * 32, NT), NT, 0, A.ptr.p, A.idx.p, A.val.p, A.n, x, y);
 }
 
