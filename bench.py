@@ -77,25 +77,39 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_oracle_sample(data, cells, steps=1):
-    """Time the CPU oracle (reference restatement) on the first `cells` columns."""
+def cpu_oracle_sample(data, cells, steps=1, threads=None):
+    """Time the CPU oracle (reference restatement) on the first `cells` columns with `threads`
+    BLAS threads (None: library default)."""
     from oracle import rsoptsc_oracle as O
     sub = np.asfortranarray(data[:, :cells])
     times = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        r = O.SimilarityM(LAMBDA, sub, literal=True)
-        O.ClusterCells(r["W"], n_clusters=RANK)
-        times.append(time.perf_counter() - t0)
+
+    def run():
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            r = O.SimilarityM(LAMBDA, sub, literal=True)
+            O.ClusterCells(r["W"], n_clusters=RANK)
+            times.append(time.perf_counter() - t0)
+    if threads:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=int(threads)):
+            run()
+    else:
+        run()
     return times
 
 
-def blas_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-    except Exception:
-        return os.cpu_count() or 1
+def best_cpu_threads(data, cells):
+    """torchrun pins OMP_NUM_THREADS=1 and an oversubscribed OpenBLAS can be slower than one thread
+    at this size: time the sample with all host threads and with one, keep the faster setting."""
+    ncpu = os.cpu_count() or 1
+    cand = sorted({1, ncpu})
+    best = None
+    for th in cand:
+        t = cpu_oracle_sample(data, cells, threads=th)[0]
+        if best is None or t < best[1]:
+            best = (th, t)
+    return best
 
 
 def run_reference(args, rank):
@@ -104,9 +118,8 @@ def run_reference(args, rank):
     from rsoptsc_b200.synthetic import synthetic_lognorm
     cells = args.cpu_cells
     data, _ = synthetic_lognorm(args.genes, max(cells, 16), seed=0)
-    for _ in range(min(args.warmup, 1)):       # one warm-up pass is enough for a CPU BLAS path
-        cpu_oracle_sample(data, cells)
-    times = cpu_oracle_sample(data, cells, steps=args.steps)
+    threads, _ = best_cpu_threads(data, cells)  # doubles as the warm-up pass; picks 1 vs all host threads
+    times = cpu_oracle_sample(data, cells, steps=args.steps, threads=threads)
     t = float(np.mean(times))
     value = cells / t
     sample = ("first %d cells x %d genes of the seed-0 synthetic matrix, full SimilarityM (literal full-SVD norms as "
@@ -118,7 +131,8 @@ def run_reference(args, rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "cells": args.cells, "genes": args.genes, "lambda": LAMBDA,
                    "nmf_rank": RANK, "reference_arm": "numpy/OpenBLAS oracle (R is not installable here)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": blas_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -269,7 +283,12 @@ def main():
             pairs = max(iops / max(flops, 1.0), 1.0)
             roof = {"kernel": "k_ozaki_gemm<8> (tcgen05.mma kind::i8, FP64-equivalent)", "bound": "tensor",
                     "achieved": flops / secs / 1e12, "peak": 2.0 * bf16 / pairs, "unit": "TFLOP/s",
-                    "frac": (flops / secs / 1e12) / (2.0 * bf16 / pairs), "traffic": None,
+                    "frac": (flops / secs / 1e12) / (2.0 * bf16 / pairs),
+                    "traffic": 13.43e9,
+                    "traffic_note": "dram read+write of ONE launch, the n=10000 Gram, from ncu --set full "
+                                    "(profiles/r1_ozaki_gemm_ncu_full.csv); its operands are 0.8 GB of int8 slices + "
+                                    "0.4 GB FP64 output, re-read per tile row/column through L2 (11 % of DRAM "
+                                    "bandwidth: the kernel is tensor-bound, tensor pipe active 65 %)",
                     "int8_tops_achieved": iops / secs / 1e12, "int8_tops_peak": 2.0 * bf16,
                     "peak_source": "2 x %s (int8 runs at twice the bf16 rate) / %d int8 slice-pair MMAs per FP64 MAC"
                                    % (bf16_src, round(pairs)),
@@ -283,9 +302,10 @@ def main():
                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                     "share_of_step": v["ms"] / 1e3 / t_dev, "launches": v["calls"]}
         cpu = None
-        if not args.no_cpu_baseline:
-            t_cpu = cpu_oracle_sample(data, args.cpu_cells)[0]
-            cpu = {"value": args.cpu_cells / t_cpu, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+        if not args.no_cpu_baseline and world == 1:
+            cpu_threads, t_cpu = best_cpu_threads(data, args.cpu_cells)
+            cpu = {"value": args.cpu_cells / t_cpu, "unit": UNIT, "cores": cpu_threads, "host_cpus": os.cpu_count(),
+                   "kind": "port",
                    "sample": "first %d cells x %d genes of the same matrix, oracle SimilarityM (literal full-SVD norms) "
                              "+ ClusterCells k=%d, %.1f s; cost ~n^3, so this overstates CPU cells/s at %d cells"
                              % (args.cpu_cells, m, RANK, t_cpu, n), "seconds": t_cpu}

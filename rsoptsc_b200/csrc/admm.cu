@@ -1,11 +1,15 @@
 // computeM: linearised ADMM for  min ||Z||_* + lambda ||E||_{2,1}  s.t. X = XZ + E, Z^T 1 = 1,
 // Z_Omega = 0   (R/SimilarityM.R:115-197), restructured for the GPU:
 //
-//   * Z lives on its kNN support only (n*K values, CSR + CSC views); the dense n x n state is
-//     Y3 and the SVT operand A/J.
+//   * Z lives on its kNN support only (n*K values, CSR + CSC views); the dense state is Y3 and
+//     the SVT operand A/J.
+//   * Y3, A and J are block diagonal over the connected components of the support graph (the SVD
+//     of a block-diagonal matrix is block diagonal, Y3 starts at 0): they are stored as the
+//     concatenated n_c x n_c blocks and the SVT runs per block (sum n_c^3 instead of n^3).
 //   * the stop test of iteration `it` (R :157-162) only looks at Err[it-1], Err[it-2] and XXZ,
 //     none of which the SVT touches, so it is evaluated BEFORE the SVT (saves one SVT).
-//   * J == 0 exactly while ||A||_F <= 1/mu (all singular values thresholded): SVT skipped.
+//   * J_c == 0 exactly while sigma_1(A_c) <= 1/mu (all singular values thresholded): SVT skipped;
+//     decided by Frobenius bounds, else by a residual-certified Lanczos value of sigma_1.
 //   * spectral norms: Lanczos (lanczos.cu); the two tests that only compare a norm with
 //     epsilon = 1e-5 use the Frobenius bounds ||.||_F/sqrt(min dim) <= ||.||_2 <= ||.||_F first.
 #include <algorithm>
@@ -121,7 +125,7 @@ void run_admm(const double* d_X, int64_t m, int64_t n, const Support& s, double 
   const double rho = 5.0, mumax = 1e6, epsilon = 1e-5;       // R :118-121
   double mu = 1e-6;
   st.m = m; st.n = n; st.X = d_X;
-  const size_t mn = (size_t)m * n, nn = (size_t)n * n;
+  const size_t mn = (size_t)m * n;
   st.Zs.alloc(std::max<size_t>(s.nnz, 1)); st.Zs.zero(c.stream);
   st.q.alloc(std::max<size_t>(s.nnz, 1));
   st.XXZ.alloc(mn); st.E.alloc(mn); st.Y1.alloc(mn); st.R.alloc(mn); st.M.alloc(mn);

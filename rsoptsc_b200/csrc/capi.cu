@@ -56,6 +56,7 @@ static std::map<size_t, std::vector<void*>>& pool() {  // leaked on purpose: sta
   return *p;
 }
 #define g_pool pool()
+static size_t g_pooled_bytes = 0;                  // bytes currently idle in the cache
 static size_t bucket_of(size_t bytes) {
   if (bytes <= 512) return 512;
   int hb = 63 - __builtin_clzll((unsigned long long)bytes);
@@ -68,6 +69,7 @@ void* pool_alloc(size_t bytes) {
   if (it != g_pool.end() && !it->second.empty()) {
     void* p = it->second.back();
     it->second.pop_back();
+    g_pooled_bytes -= std::min(g_pooled_bytes, b);
     return p;
   }
   void* p = nullptr;
@@ -81,13 +83,26 @@ void* pool_alloc(size_t bytes) {
     fail(2, __FILE__, __LINE__, std::string("CUDA: cudaMalloc of ") + std::to_string(b) + " bytes failed: " + cudaGetErrorString(e));
   return p;
 }
+static size_t pool_limit() {                       // idle bytes above which the cache is handed back
+  static size_t lim = 0;
+  if (!lim) {
+    const char* e = getenv("RSOPTSC_POOL_LIMIT_GB");
+    lim = (size_t)((e ? atof(e) : 48.0) * (double)(1ull << 30));
+  }
+  return lim;
+}
 void pool_free(void* p, size_t bytes) {
-  if (p) g_pool[bucket_of(bytes)].push_back(p);
+  if (!p) return;
+  const size_t b = bucket_of(bytes);
+  g_pool[b].push_back(p);
+  g_pooled_bytes += b;
+  if (g_pooled_bytes > pool_limit()) pool_trim();
 }
 void pool_trim() {
   for (auto& kv : g_pool)
     for (void* p : kv.second) cudaFree(p);
   g_pool.clear();
+  g_pooled_bytes = 0;
 }
 
 // ---- phase timers ---------------------------------------------------------------------

@@ -20,18 +20,8 @@ __global__ void k_inv_sqrt(double* __restrict__ d, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * ET + threadIdx.x;
   if (i < n) d[i] = 1.0 / sqrt(d[i]);
 }
-// L = I - (dd_i * S_ij) * dd_j      (R/Clustering.R:99-101; sqrtm/solve of a diagonal matrix, quirk Q13)
-__global__ void k_laplacian(const double* __restrict__ S, const double* __restrict__ dd, int64_t n,
-                            double* __restrict__ L) {
-  const int64_t j = blockIdx.y;
-  const double dj = dd[j];
-  for (int64_t i = (int64_t)blockIdx.x * ET + threadIdx.x; i < n; i += (int64_t)gridDim.x * ET) {
-    const double v = (dd[i] * S[i + j * n]) * dj;
-    L[i + j * n] = (i == j ? 1.0 : 0.0) - v;
-  }
-}
-
-// diagonal block of the Laplacian over the cells `members` (ascending): Lc[a,b] = delta - (dd_i S_ij) dd_j
+// L = I - (dd_i * S_ij) * dd_j      (R/Clustering.R:99-101; sqrtm/solve of a diagonal matrix, quirk Q13):
+// diagonal block of the Laplacian over the cells `members` (ascending)
 __global__ void k_laplacian_block(const double* __restrict__ S, const double* __restrict__ dd, int64_t n,
                                   const int* __restrict__ members, int64_t nc, double* __restrict__ Lc) {
   const int64_t b = blockIdx.y;

@@ -74,16 +74,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Same MMA with the descriptors given as (lo, hi) words: hi is constant for the whole kernel and lo
-// advances by a compile-time offset per slice, so the single issuing thread spends ~6
-// instructions per MMA (the tensor pipe needs a new M128 N128 K32 MMA every 64 cycles).
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::i8 (s8 x s8 -> s32).  The 64-bit shared-memory matrix
+// descriptors are given as (lo, hi) words: hi is constant for the whole kernel and lo advances by a
+// compile-time offset per slice, so the single issuing thread spends ~6 instructions per MMA (the
+// tensor pipe needs a new M128 N128 K32 MMA every 64 cycles).
 __device__ __forceinline__ void umma_i8_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
@@ -97,15 +91,10 @@ __device__ __forceinline__ void umma_i8_lohi(uint32_t tmem_d, uint32_t a_lo, uin
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major operand tile, SWIZZLE_32B: rows at a 32-byte pitch, 8-row atoms of 256 B (SBO), version 1 (sm_100)
-__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(256 >> 4) << 32;
-  d |= 1ull << 46;
-  d |= 6ull << 61;
-  return d;
-}
+// Shared-memory matrix descriptor of a K-major operand tile in SWIZZLE_32B layout (rows at a 32-byte
+// pitch, 8-row atoms of 256 B):  bits [0,14) start address >> 4 | [32,46) stride byte offset >> 4 =
+// 256 >> 4 | [46,48) version = 1 (sm_100) | [61,64) layout type = 6 (SWIZZLE_32B).  The kernel builds
+// the low word per slice ((addr & 0x3FFFF) >> 4) and keeps the high word constant (desc_hi).
 // kind::i8 instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N = 128, M = 128
 __device__ __forceinline__ uint32_t make_idesc() {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);

@@ -253,6 +253,47 @@ def test_full_size_properties_config2():
     assert ari > 0.5, ari
 
 
+def test_similarity_forced_K_and_lambda():
+    """config 5 forces K = 30; the vignette uses lambda = 0.05."""
+    p = small_problem(200, 260, seed=31)
+    ref = O.SimilarityM(0.05, p["data"], embedding=p["emb"], literal=False, K=12)
+    got = api.SimilarityM(0.05, p["data"], embedding=p["emb"], K=12)
+    assert got["K"] == 12 and got["iters"] == ref["iters"]
+    assert relF(got["W"], ref["W"]) < 1e-6
+    assert (np.count_nonzero(got["W"], axis=1) >= 1).all()
+
+
+def test_error_paths_return_status_not_crash():
+    import ctypes as C
+    from rsoptsc_b200 import _lib
+    lib = _lib.init()
+    x = np.ones((4, 4), order="F")
+    out = np.empty_like(x)
+    dp = lambda a: a.ctypes.data_as(_lib.c_double_p)  # noqa: E731
+    assert lib.rsoptsc_normalize(dp(x), 0, 4, dp(out)) != 0                 # empty matrix
+    assert b"empty" in lib.rsoptsc_last_error()
+    idx = np.full((4, 2), 9, dtype=np.int32)                                  # neighbour index out of range
+    E, it, st = C.c_double(0), C.c_int32(0), C.c_int32(0)
+    rc = lib.rsoptsc_computeM(dp(x), 4, 4, idx.ctypes.data_as(_lib.c_int32_p), 2, 0.5, None, C.byref(E), C.byref(it),
+                              C.byref(st), None)
+    assert rc != 0 and b"out of range" in lib.rsoptsc_last_error()
+    with pytest.raises(_lib.RsoptscError):
+        api.nmf_lee(np.eye(5), 9)                                             # rank > n
+    with pytest.raises(_lib.RsoptscError):
+        api.knn(np.zeros((5, 3)), 40)                                         # K > 32
+    # the library still works after errors (no poisoned state)
+    assert np.allclose(api.normalize(np.arange(12.0).reshape(3, 4) + 1).sum(), api.normalize(np.arange(12.0).reshape(3, 4) + 1).sum())
+
+
+def test_repeated_calls_are_deterministic():
+    """Caching allocator / persistent workspaces: same inputs -> bit-identical outputs, run to run."""
+    p = small_problem(120, 300, seed=8)
+    a = api.computeM(None, p["X"], 0.5, idx=p["idx"])
+    api.nmf_lee(np.eye(40) + 0.01, 3)               # interleave a different workload
+    b = api.computeM(None, p["X"], 0.5, idx=p["idx"])
+    assert a["iters"] == b["iters"] and np.array_equal(a["Z"], b["Z"]) and a["E"] == b["E"]
+
+
 def test_ozaki_gemm_matches_fp64():
     """tcgen05 split-integer GEMM vs numpy FP64, error measured against |A||B| (DGEMM-style bound)."""
     import ctypes as C
