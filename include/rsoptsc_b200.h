@@ -144,6 +144,18 @@ int rsoptsc_count_clusters(const double* S, int64_t n, double tol, int32_t range
                            int32_t range_hi, int32_t n_comp, int32_t* upper_bound,
                            int32_t* lower_bound, double* vals, int32_t* n_eigs);
 
+/* ---- RepresentationMap pieces (R/RepresentationMap.R) --------- */
+/* stats::dist(flat_embedding, "euclidean") as a full matrix (:57); emb: n x dim, dist: n x n */
+int rsoptsc_dist_flat(const double* emb, int64_t n, int32_t dim, double* dist);
+/* adj[S > 0] = 1; diag(adj) = 0 (:59-62); S, adj: n x n */
+int rsoptsc_adjacency(const double* S, int64_t n, double* adj);
+/* igraph::components of the undirected graph of adj (:64-66): membership 1-based, numbered by
+ * the lowest vertex of each component; edge {i,j} iff adj[i,j] != 0 or adj[j,i] != 0 */
+int rsoptsc_graph_components(const double* adj, int64_t n, int32_t* membership,
+                             int32_t* n_components);
+/* igraph::distances(graph) (:89): all-pairs unweighted shortest path lengths, Inf if unreachable */
+int rsoptsc_graph_distances(const double* adj, int64_t n, double* dist);
+
 /* ---- dense contraction backends (a4 Gram / reconstruction GEMMs) --------------------- */
 /* backend: 0 = cuBLAS FP64 (library baseline), 1 = tcgen05 split-integer (Ozaki) GEMM for
  * contractions with every dimension >= 1536 (default), 2 = Ozaki wherever legal (>= 256). */

@@ -392,3 +392,47 @@ def CountClusters(data, tol=0.01, rng=range(2, 21), n_comp=3):
     lower = int(np.sum(eigs["val"] <= tol))                 # :78
     return dict(upper_bound=upper if len(upper) > 1 else int(upper[0]), lower_bound=lower,
                 eigs=eigs, tau=tau, solo_count=solo)
+
+
+# --------------------------------------------------------------------------------------
+# RepresentationMap dense / graph pieces  (R/RepresentationMap.R:37-39,57-66,89)
+# parity unpinned: the reference's only test of this function is skipped (testPtime.R:4)
+# --------------------------------------------------------------------------------------
+def dist_flat(emb):
+    """as.matrix(dist(flat_embedding, 'euclidean')) (:57): R accumulates dev*dev column by column."""
+    P = np.asarray(emb, dtype=np.float64)
+    acc = np.zeros((P.shape[0], P.shape[0]))
+    for c in range(P.shape[1]):
+        dev = P[:, c][:, None] - P[:, c][None, :]
+        acc = acc + dev * dev
+    return np.sqrt(acc)
+
+
+def adjacency(S):
+    """:59-62."""
+    A = (np.asarray(S) > 0).astype(np.float64)
+    np.fill_diagonal(A, 0.0)
+    return A
+
+
+def graph_components(adj):
+    """igraph::components of the undirected graph (:64-66): membership numbered by lowest vertex, 1-based."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import connected_components
+    A = sp.csr_matrix((np.asarray(adj) != 0) | (np.asarray(adj).T != 0))
+    nc, lab = connected_components(A, directed=False)
+    order = {}
+    mem = np.empty(len(lab), dtype=np.int32)
+    for v, c in enumerate(lab):
+        if c not in order:
+            order[c] = len(order) + 1
+        mem[v] = order[c]
+    return dict(membership=mem, csize=np.bincount(mem)[1:], no=int(nc))
+
+
+def graph_distances(adj):
+    """igraph::distances (:89): unweighted all-pairs shortest paths, Inf when unreachable."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import shortest_path
+    A = sp.csr_matrix(((np.asarray(adj) != 0) | (np.asarray(adj).T != 0)).astype(np.float64))
+    return shortest_path(A, method="D", directed=False, unweighted=True)

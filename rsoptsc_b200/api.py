@@ -207,6 +207,60 @@ def ClusterCells(similarityMatrix=None, n_clusters=None, n_comp=3, max_iter=2000
     return dict(H=r["W"], labels=r["labels"], ensemble=ensemble, iters=r["iters"], coef=r["H"])
 
 
+def dist_flat(flat_embedding):
+    """as.matrix(dist(flat_embedding, method='euclidean')) of R/RepresentationMap.R:57."""
+    lib = _lib.init()
+    e = _f64(flat_embedding)
+    n, dim = e.shape
+    out = np.empty((n, n), dtype=np.float64, order="F")
+    _lib.check(lib.rsoptsc_dist_flat(_dp(e), n, dim, _dp(out)))
+    return out
+
+
+def adjacency(similarity_matrix):
+    """adj[S > 0] = 1; diag(adj) = 0 of R/RepresentationMap.R:59-62."""
+    lib = _lib.init()
+    s = _f64(similarity_matrix)
+    n = s.shape[0]
+    out = np.empty((n, n), dtype=np.float64, order="F")
+    _lib.check(lib.rsoptsc_adjacency(_dp(s), n, _dp(out)))
+    return out
+
+
+def graph_components(adj):
+    """igraph::components(graph_from_adjacency_matrix(adj, 'undirected')) -> dict(membership 1-based, csize, no)."""
+    lib = _lib.init()
+    a = _f64(adj)
+    n = a.shape[0]
+    mem = np.empty(n, dtype=np.int32)
+    no = C.c_int32(0)
+    _lib.check(lib.rsoptsc_graph_components(_dp(a), n, _ip(mem), C.byref(no)))
+    return dict(membership=mem, csize=np.bincount(mem)[1:], no=int(no.value))
+
+
+def graph_distances(adj):
+    """igraph::distances(graph) (unweighted all-pairs shortest paths, Inf when unreachable)."""
+    lib = _lib.init()
+    a = _f64(adj)
+    n = a.shape[0]
+    out = np.empty((n, n), dtype=np.float64, order="F")
+    _lib.check(lib.rsoptsc_graph_distances(_dp(a), n, _dp(out)))
+    return out
+
+
+def RepresentationMap(flat_embedding, similarity_matrix, join_components=False, normalize_S=True):
+    """Dense/graph part of RepresentationMap (R/RepresentationMap.R:30-100) for a given 2-D
+    `flat_embedding` (umap/Rtsne stay in R, as does JoinGraphComponents): returns dist_flat,
+    adj_matrix, components, n_components, dist_graph.  normalize_S only rescales S by its sum
+    (:37-39) and does not change the S > 0 pattern."""
+    if join_components:
+        raise NotImplementedError("JoinGraphComponents stays in R host code (SURVEY.md section 2)")
+    adj = adjacency(similarity_matrix)
+    comps = graph_components(adj)
+    return dict(dist_flat=dist_flat(flat_embedding), adj_matrix=adj, components=comps, n_components=comps["no"],
+                dist_graph=graph_distances(adj), flat_embedding=flat_embedding)
+
+
 class DeviceBuffer:
     """Library-owned device allocation (for the *_dev entry points: inputs resident in HBM)."""
 

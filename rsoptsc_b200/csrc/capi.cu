@@ -539,6 +539,50 @@ int rsoptsc_count_clusters(const double* S, int64_t n, double tol, int32_t range
   });
 }
 
+// ---- RepresentationMap pieces --------------------------------------------------------------
+int rsoptsc_dist_flat(const double* emb, int64_t n, int32_t dim, double* dist) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(n > 0 && dim > 0, "dist_flat: empty embedding");
+    DevBuf<double> e((size_t)n * dim), d((size_t)n * n);
+    e.upload(emb, (size_t)n * dim, s);
+    dist_flat(e.p, n, dim, d.p);
+    d.download(dist, (size_t)n * n, s);
+    RS_CUDA(cudaStreamSynchronize(s));
+  });
+}
+int rsoptsc_adjacency(const double* S, int64_t n, double* adj) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(n > 0, "adjacency: empty matrix");
+    DevBuf<double> d((size_t)n * n), a((size_t)n * n);
+    d.upload(S, (size_t)n * n, s);
+    adjacency(d.p, n, a.p);
+    a.download(adj, (size_t)n * n, s);
+    RS_CUDA(cudaStreamSynchronize(s));
+  });
+}
+int rsoptsc_graph_components(const double* adj, int64_t n, int32_t* membership, int32_t* n_components) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(n > 0, "graph_components: empty matrix");
+    DevBuf<double> a((size_t)n * n);
+    a.upload(adj, (size_t)n * n, s);
+    graph_components(a.p, n, membership, n_components);
+  });
+}
+int rsoptsc_graph_distances(const double* adj, int64_t n, double* dist) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(n > 0, "graph_distances: empty matrix");
+    DevBuf<double> a((size_t)n * n), d((size_t)n * n);
+    a.upload(adj, (size_t)n * n, s);
+    graph_distances(a.p, n, d.p);
+    d.download(dist, (size_t)n * n, s);
+    RS_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
 int rsoptsc_set_gemm_backend(int32_t backend) {
   return guarded([&] {
     RS_REQUIRE(backend >= 0 && backend <= 2, "gemm backend must be 0 (cublas), 1 (ozaki, large only) or 2 (ozaki, forced)");

@@ -142,7 +142,7 @@ __global__ void k_scale_vec(double* __restrict__ v, int64_t n, double f) {
   if (i < n) v[i] *= f;
 }
 
-static void pca_scores_sparse(const Compressed& csr, const Compressed& csc, int64_t n, int ncomp, double* d_scores) {
+static bool pca_scores_sparse(const Compressed& csr, const Compressed& csc, int64_t n, int ncomp, double* d_scores) {
   Phase ph("pca");
   const unsigned g = (unsigned)cdiv(n, ET);
   DevBuf<double> ones(n), mu(n), t(n), scal(2);
@@ -168,7 +168,7 @@ static void pca_scores_sparse(const Compressed& csr, const Compressed& csc, int6
     lz.advance(next - lz.steps);
     lz.ritz(theta, S, /*last_row_only=*/true);
     const int st = lz.steps;
-    RS_REQUIRE(st >= ncomp, "count_clusters: similarity matrix has fewer than n_comp non-trivial components");
+    if (st < ncomp) return false;  // Krylov space exhausted (repeated singular values): caller goes dense
     bool conv = true;
     for (int i = 0; i < ncomp && conv; ++i)
       conv = std::fabs(lz.beta[st - 1] * S[st - 1 - i]) <= 1e-13 * theta[st - 1];
@@ -181,6 +181,7 @@ static void pca_scores_sparse(const Compressed& csr, const Compressed& csc, int6
   lz.ritz_vectors(S, sel, V.p);
   for (int i = 0; i < ncomp; ++i) tc_mul(V.p + (size_t)i * n, d_scores + (size_t)i * n);
   RS_CUDA(cudaStreamSynchronize(ctx().stream));
+  return true;
 }
 
 void get_components(const double* d_S, int64_t n, double tol, double* h_vals, int32_t* n_eigs) {
@@ -553,9 +554,7 @@ void count_clusters(const double* d_S, int64_t n, double tol, int lo, int hi, in
   const double tau = solo <= 5 ? 0.3 : (solo <= 10 ? 0.4 : 0.5);          // R :64-70
   // GetEnsemble (R :125-154): PCA scores of t(S), PAM for every k in range, consensus
   DevBuf<double> scores((size_t)n * n_comp);
-  if (csr.nnz <= 128 * n) {
-    pca_scores_sparse(csr, csc, n, n_comp, scores.p);                     // R :133 (sparse similarity)
-  } else {
+  if (!(csr.nnz <= 128 * n && pca_scores_sparse(csr, csc, n, n_comp, scores.p))) {  // R :133, sparse route first
     std::vector<double> eig;
     pca_spectrum(d_S, n, n, eig, scores.p, n_comp);                       // R :133 (dense similarity)
   }

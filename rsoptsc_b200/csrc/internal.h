@@ -117,6 +117,12 @@ struct NmfResult { int iters = 0; };
 void nmf_lee(const double* d_V, int64_t n, int k, int max_iter, double* h_basis, double* h_coef,
              int32_t* h_labels, NmfResult& res);
 
+// graph.cu (RepresentationMap pieces)
+void dist_flat(const double* d_emb, int64_t n, int dim, double* d_D);
+void adjacency(const double* d_S, int64_t n, double* d_A);
+void graph_components(const double* d_adj, int64_t n, int32_t* h_membership, int32_t* n_components);
+void graph_distances(const double* d_adj, int64_t n, double* d_D);
+
 // eigengap.cu
 void get_components(const double* d_S, int64_t n, double tol, double* h_vals, int32_t* n_eigs);
 void consensus_dense(const int32_t* d_labels, int R, int64_t n, double tau, double* d_consen);

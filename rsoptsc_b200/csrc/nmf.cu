@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 
+#include "gemm.h"
 #include "internal.h"
 #include "lanczos.h"
 #include "sparse.h"
@@ -201,8 +202,8 @@ __global__ void k_argmax(const double* __restrict__ F, int64_t n, int k, int bas
 }
 
 // ---- NNDSVD seed ----------------------------------------------------------------------------
-static void nndsvd_seed(const Compressed& csr, const Compressed& csc, int64_t n, int k, std::vector<double>& W0,
-                        std::vector<double>& H0) {
+static void nndsvd_seed(const double* d_V, const Compressed& csr, const Compressed& csc, int64_t n, int k,
+                        std::vector<double>& W0, std::vector<double>& H0) {
   Phase ph("nndsvd");
   cudaStream_t s = ctx().stream;
   // top-k singular triplets of V: Lanczos on V^T V (two SpMVs per step)
@@ -215,11 +216,14 @@ static void nndsvd_seed(const Compressed& csr, const Compressed& csc, int64_t n,
   });
   std::vector<double> theta, S;
   int next = std::min(cap, std::max(2 * k + 24, 48));
+  bool dense_fallback = false;
   while (true) {
     lz.advance(next - lz.steps);
     lz.ritz(theta, S, /*last_row_only=*/true);
     const int st = lz.steps;
-    RS_REQUIRE(st >= k, "nmf: matrix rank is below the requested factorisation rank");
+    // A single-vector Krylov space sees each DISTINCT singular value once: with (numerically)
+    // repeated singular values it is exhausted before k triplets exist -> dense path below.
+    if (st < k) { dense_fallback = true; break; }
     const double top = theta[st - 1];
     bool conv = true;
     for (int i = 0; i < k && conv; ++i) {
@@ -229,11 +233,33 @@ static void nndsvd_seed(const Compressed& csr, const Compressed& csc, int64_t n,
     if (conv || lz.exhausted || st >= lz.max_steps) { lz.ritz(theta, S); break; }
     next = std::min(lz.max_steps, st + std::max(32, st / 3));
   }
-  const int st = lz.steps;
   std::vector<int> sel(k);
-  for (int i = 0; i < k; ++i) sel[i] = st - 1 - i;  // descending sigma
   DevBuf<double> Vr((size_t)n * k), Ur((size_t)n * k);
-  lz.ritz_vectors(S, sel, Vr.p);
+  if (!dense_fallback) {
+    const int st = lz.steps;
+    for (int i = 0; i < k; ++i) sel[i] = st - 1 - i;  // descending sigma
+    lz.ritz_vectors(S, sel, Vr.p);
+  } else {
+    // dense eigen-decomposition of V^T V (the reference takes a full SVD of V anyway)
+    RS_REQUIRE(n <= 8192, "nmf: repeated singular values need the dense NNDSVD path, limited to n <= 8192");
+    Context& c = ctx();
+    DevBuf<double> G((size_t)n * n), lam(n);
+    gram_AtA(d_V, n, n, G.p);
+    int lwork = 0;
+    RS_CUSOLVER(cusolverDnDsyevd_bufferSize(c.cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, G.p,
+                                            (int)n, lam.p, &lwork));
+    DevBuf<double> work((size_t)std::max(lwork, 1));
+    DevBuf<int> info(1);
+    RS_CUSOLVER(cusolverDnDsyevd(c.cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, G.p, (int)n,
+                                 lam.p, work.p, lwork, info.p));
+    theta.assign(n, 0.0);
+    RS_CUDA(cudaMemcpyAsync(theta.data(), lam.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    for (int i = 0; i < k; ++i) {
+      sel[i] = (int)n - 1 - i;
+      RS_CUDA(cudaMemcpyAsync(Vr.p + (size_t)i * n, G.p + (size_t)sel[i] * n, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+    }
+    RS_CUDA(cudaStreamSynchronize(s));
+  }
   for (int i = 0; i < k; ++i) spmv(csr, Vr.p + (size_t)i * n, Ur.p + (size_t)i * n);  // sigma_i u_i = V v_i
   std::vector<double> hv((size_t)n * k), hu((size_t)n * k);
   Vr.download(hv.data(), hv.size(), s);
@@ -292,7 +318,7 @@ void nmf_lee(const double* d_V, int64_t n, int k, int max_iter, double* h_basis,
   compress(d_V, n, true, csr);
   compress(d_V, n, false, csc);
   std::vector<double> W0, H0;
-  nndsvd_seed(csr, csc, n, k, W0, H0);
+  nndsvd_seed(d_V, csr, csc, n, k, W0, H0);
   Phase ph("nmf");
   DevBuf<double> W((size_t)n * k), H((size_t)n * k), G((size_t)k * k), part((size_t)GP * std::max(k * k, k));
   DevBuf<int32_t> idxA(n), idxB(n);
@@ -307,7 +333,9 @@ void nmf_lee(const double* d_V, int64_t n, int k, int max_iter, double* h_basis,
   int inc = 0, it = 0;
   int32_t* cur = idxA.p;
   int32_t* prev = idxB.p;
-  for (it = 1; it <= max_iter; ++it) {
+  if (upd_smem > 48 * 1024)
+    RS_CUDA(cudaFuncSetAttribute(k_mult_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
+  auto one_iteration = [&] {
     // H update: numerator W^T V by columns (CSC), denominator (W^T W) H
     RS_LAUNCH(k_gram_partial, GP, NT, gram_smem, W.p, n, k, part.p);
     RS_LAUNCH(k_gram_final, (unsigned)cdiv(kk, NT), NT, 0, part.p, GP, kk, G.p);
@@ -319,6 +347,36 @@ void nmf_lee(const double* d_V, int64_t n, int k, int max_iter, double* h_basis,
     // rescale columns of W to sum 1
     RS_LAUNCH(k_colsum_partial, GP, NT, 0, W.p, n, k, part.p);
     RS_LAUNCH(k_rescale, 148 * 2, NT, 0, W.p, n, k, part.p, GP);
+  };
+  // The loop is launch-bound (8 small kernels per iteration): the `check_interval` iterations between
+  // two stop checks are captured once into a CUDA graph and replayed.
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  const int64_t launches_before = g_launches.load();
+  RS_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  try {
+    for (int r = 0; r < check_interval; ++r) one_iteration();
+  } catch (...) {
+    cudaStreamEndCapture(s, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    throw;
+  }
+  RS_CUDA(cudaStreamEndCapture(s, &graph));
+  const int64_t launches_per_graph = g_launches.load() - launches_before;
+  g_launches.fetch_sub(launches_per_graph);  // captured, not executed
+  RS_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+  struct GraphGuard {
+    cudaGraph_t g; cudaGraphExec_t e;
+    ~GraphGuard() { if (e) cudaGraphExecDestroy(e); if (g) cudaGraphDestroy(g); }
+  } guard{graph, gexec};
+  for (it = 1; it <= max_iter; ++it) {
+    if ((it - 1) % check_interval == 0 && it + check_interval - 1 <= max_iter) {
+      RS_CUDA(cudaGraphLaunch(gexec, s));          // iterations it .. it + check_interval - 1
+      g_launches.fetch_add(launches_per_graph);
+      it += check_interval - 1;
+    } else {
+      one_iteration();
+    }
     if (it % check_interval == 0) {  // 'connectivity' stop on the coef arg-max
       changed.zero(s);
       RS_LAUNCH(k_argmax, (unsigned)cdiv(n, NT), NT, 0, H.p, n, k, 0, cur, have_prev ? prev : (const int32_t*)nullptr,

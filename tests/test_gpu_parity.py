@@ -253,6 +253,35 @@ def test_full_size_properties_config2():
     assert ari > 0.5, ari
 
 
+# ---- RepresentationMap pieces -----------------------------------------------------
+def test_representation_map_pieces_fixture(joost):
+    S = joost["S"]
+    rng = np.random.default_rng(0)
+    emb = rng.normal(size=(joost["n"], 2))
+    got = api.RepresentationMap(emb, S)
+    assert np.array_equal(got["dist_flat"], O.dist_flat(emb))               # bit-exact (no FMA, same order)
+    assert np.array_equal(got["adj_matrix"], O.adjacency(S))
+    ref_c = O.graph_components(O.adjacency(S))
+    assert got["n_components"] == ref_c["no"] == 6                          # == n_eigs of GetComponents
+    assert np.array_equal(got["components"]["membership"], ref_c["membership"])
+    assert np.array_equal(got["components"]["csize"], ref_c["csize"])
+    assert np.array_equal(got["dist_graph"], O.graph_distances(O.adjacency(S)))   # integers / Inf
+
+
+@pytest.mark.parametrize("n", [1, 2, 257, 1500])
+def test_graph_distances_random(n):
+    rng = np.random.default_rng(n)
+    A = (rng.random((n, n)) < min(1.0, 2.5 / max(n, 1))).astype(np.float64)   # sparse, directed input
+    np.fill_diagonal(A, 0)
+    got = api.graph_distances(A)
+    ref = O.graph_distances(A)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(got, got.T)
+    c = api.graph_components(A)
+    assert c["no"] == O.graph_components(A)["no"]
+    assert np.array_equal(np.isfinite(got), c["membership"][:, None] == c["membership"][None, :])
+
+
 def test_similarity_forced_K_and_lambda():
     """config 5 forces K = 30; the vignette uses lambda = 0.05."""
     p = small_problem(200, 260, seed=31)
