@@ -156,6 +156,14 @@ int rsoptsc_graph_components(const double* adj, int64_t n, int32_t* membership,
 /* igraph::distances(graph) (:89): all-pairs unweighted shortest path lengths, Inf if unreachable */
 int rsoptsc_graph_distances(const double* adj, int64_t n, double* dist);
 
+/* ---- GetSignalingPartners core (R/Signaling.R:75-163,291-293) ---- */
+/* P[i,j] (n x n, i = ligand cell, j = receptor cell) for one ligand-receptor pair: lig, rec = the
+ * two expression rows (n); beta / gamma = per-cell up / down target terms (getBetaj / getGammaj),
+ * NULL when the receptor has no up / down targets; normalize != 0 divides every row by its sum
+ * (NaN -> 0) as GetSignalingPartners does. */
+int rsoptsc_signaling_pair(const double* lig, const double* rec, const double* beta,
+                           const double* gamma, int64_t n, int32_t normalize, double* P);
+
 /* ---- dense contraction backends (a4 Gram / reconstruction GEMMs) --------------------- */
 /* backend: 0 = cuBLAS FP64 (library baseline), 1 = tcgen05 split-integer (Ozaki) GEMM for
  * contractions with every dimension >= 1536 (default), 2 = Ozaki wherever legal (>= 256). */

@@ -16,6 +16,7 @@ R/sysdata.rda by tests/golden/make_golden.py):
                           order, eps, rescale and the connectivity stop rule)
     * CountClusters       upper_bound == 9 == ncol(joostTest$H) (consistency, not an assertion
                           of the reference)
+    * GetSignalingPartners  P[[1]] == the hand-computed 3-cell answer of tests/testthat/testSignal.R:16-81
   PARITY UNPINNED (restated from the published algorithms of third-party packages that
   are not vendored in the reference: NMF (renozao/NMF@devel, >= 0.23), cluster >= 2.0.7-1,
   FNN >= 1.1.2.1):
@@ -428,6 +429,64 @@ def graph_components(adj):
             order[c] = len(order) + 1
         mem[v] = order[c]
     return dict(membership=mem, csize=np.bincount(mem)[1:], no=int(nc))
+
+
+# --------------------------------------------------------------------------------------
+# GetSignalingPartners  (R/Signaling.R:1-60, 75-163, 187-309) -- pinned by the hand-computed
+# known answer of tests/testthat/testSignal.R:16-81 (tests/test_oracle_golden.py)
+# --------------------------------------------------------------------------------------
+def signaling_pair(lig, rec, beta=None, gamma=None, normalize=True):
+    """One ligand-receptor pair: updateFlat{Both,Up,Down,None} (:75-163) + row normalisation (:291-293).
+    Scalar loops follow getAlpha/getK/getD literally (pure Python: small cases only)."""
+    lig = np.asarray(lig, dtype=np.float64); rec = np.asarray(rec, dtype=np.float64)
+    n = len(lig)
+    P = np.zeros((n, n))
+    for i in range(n):
+        for j in range(n):
+            a = 0.0 if (lig[i] == 0 or rec[j] == 0) else np.exp(-1.0 / (lig[i] * rec[j]))     # getAlpha
+            v = a
+            if beta is not None:
+                b = beta[j]
+                v = v * (0.0 if (a == 0 and b == 0) else a / (a + b))                         # getK
+            if gamma is not None:
+                g = gamma[j]
+                v = v * (0.0 if (a == 0 and g == 0) else a / (a + g))                         # getD
+            if beta is not None:
+                v = v * beta[j]
+            if gamma is not None:
+                v = v * gamma[j]
+            P[i, j] = v
+    if normalize:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            P = P / P.sum(axis=1, keepdims=True)
+        P[np.isnan(P)] = 0.0
+    return P
+
+
+def GetSignalingPartners(data, gene_names, ligrec, rectarg):
+    """R/Signaling.R:187-309 with the pathway given as (ligand, receptor) pairs and
+    (receptor, target, direction) rows."""
+    data = np.asarray(data, dtype=np.float64)
+    row = {str(g).lower(): i for i, g in enumerate(gene_names)}
+    P, LR = [], []
+    for lig, rec in ligrec:
+        lig, rec = str(lig).lower(), str(rec).lower()
+        ups = sorted({str(t).lower() for r, t, d in rectarg if str(r).lower() == rec and d == "up"})
+        downs = sorted({str(t).lower() for r, t, d in rectarg if str(r).lower() == rec and d == "down"})
+        beta = gamma = None
+        if ups:                                                                              # getBetaj :43-50
+            s = data[[row[t] for t in ups]].sum(axis=0)
+            beta = np.array([0.0 if v == 0 else np.exp(-len(ups) / v) for v in s])
+        if downs:                                                                            # getGammaj :53-60
+            s = data[[row[t] for t in downs]].sum(axis=0)
+            gamma = np.array([0.0 if v == 0 else np.exp(-v / len(downs)) for v in s])
+        P.append(signaling_pair(data[row[lig]], data[row[rec]], beta, gamma, normalize=True))
+        LR.append((lig, rec))
+    tot = sum(P)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tot = tot / tot.sum(axis=1, keepdims=True)
+    tot[np.isnan(tot)] = 0.0
+    return dict(P=P, P_tot=tot, LR=LR)
 
 
 def graph_distances(adj):

@@ -261,6 +261,52 @@ def RepresentationMap(flat_embedding, similarity_matrix, join_components=False, 
                 dist_graph=graph_distances(adj), flat_embedding=flat_embedding)
 
 
+def signaling_pair(lig, rec, beta=None, gamma=None, normalize=True):
+    """P (n x n) of one ligand-receptor pair: updateFlat{Both,Up,Down,None} + row normalisation
+    (R/Signaling.R:75-163, :291-293)."""
+    lib = _lib.init()
+    lg, rc = np.ascontiguousarray(lig, dtype=np.float64), np.ascontiguousarray(rec, dtype=np.float64)
+    n = lg.shape[0]
+    b = None if beta is None else np.ascontiguousarray(beta, dtype=np.float64)
+    g = None if gamma is None else np.ascontiguousarray(gamma, dtype=np.float64)
+    P = np.empty((n, n), dtype=np.float64, order="F")
+    _lib.check(lib.rsoptsc_signaling_pair(_dp(lg), _dp(rc), _dp(b) if b is not None else None,
+                                          _dp(g) if g is not None else None, n, 1 if normalize else 0, _dp(P)))
+    return P
+
+
+def GetSignalingPartners(data, gene_names, ligrec, rectarg):
+    """GetSignalingPartners (R/Signaling.R:187-309) for an expression matrix `data` (genes x cells),
+    its row names, a list of (ligand, receptor) pairs and a list of (receptor, target, direction)
+    rows with direction in {'up', 'down'}.  Table handling (dplyr in the reference) and the O(t n)
+    target terms getBetaj/getGammaj (:43-60) are host glue; every n x n matrix is computed on the GPU.
+    Returns dict(P=[n x n per pair], P_tot=n x n, LR=[(lig, rec)])."""
+    data = np.asarray(data, dtype=np.float64)
+    row = {str(g).lower(): i for i, g in enumerate(gene_names)}
+    P, LR = [], []
+    for lig, rec in ligrec:
+        lig, rec = str(lig).lower(), str(rec).lower()
+        ups = sorted({str(t).lower() for r, t, d in rectarg if str(r).lower() == rec and d == "up"})
+        downs = sorted({str(t).lower() for r, t, d in rectarg if str(r).lower() == rec and d == "down"})
+        beta = gamma = None
+        with np.errstate(divide="ignore", invalid="ignore"):
+            if ups:
+                s = data[[row[t] for t in ups]].sum(axis=0)
+                beta = np.where(s == 0, 0.0, np.exp(-len(ups) / s))          # getBetaj
+            if downs:
+                s = data[[row[t] for t in downs]].sum(axis=0)
+                gamma = np.where(s == 0, 0.0, np.exp(-s / len(downs)))       # getGammaj
+        P.append(signaling_pair(data[row[lig]], data[row[rec]], beta, gamma, normalize=True))
+        LR.append((lig, rec))
+    tot = np.zeros_like(P[0])
+    for p in P:
+        tot = tot + p
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tot = tot / tot.sum(axis=1, keepdims=True)
+    tot[np.isnan(tot)] = 0.0
+    return dict(P=P, P_tot=tot, LR=LR)
+
+
 class DeviceBuffer:
     """Library-owned device allocation (for the *_dev entry points: inputs resident in HBM)."""
 

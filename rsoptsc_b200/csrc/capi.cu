@@ -583,6 +583,22 @@ int rsoptsc_graph_distances(const double* adj, int64_t n, double* dist) {
   });
 }
 
+int rsoptsc_signaling_pair(const double* lig, const double* rec, const double* beta, const double* gamma, int64_t n,
+                           int32_t normalize, double* P) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(n > 0, "signaling_pair: empty input");
+    DevBuf<double> l(n), r(n), b, g, p((size_t)n * n);
+    l.upload(lig, n, s);
+    r.upload(rec, n, s);
+    if (beta) { b.alloc(n); b.upload(beta, n, s); }
+    if (gamma) { g.alloc(n); g.upload(gamma, n, s); }
+    signaling_pair(l.p, r.p, b.p, g.p, n, normalize != 0, p.p);
+    p.download(P, (size_t)n * n, s);
+    RS_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
 int rsoptsc_set_gemm_backend(int32_t backend) {
   return guarded([&] {
     RS_REQUIRE(backend >= 0 && backend <= 2, "gemm backend must be 0 (cublas), 1 (ozaki, large only) or 2 (ozaki, forced)");

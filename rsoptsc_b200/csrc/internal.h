@@ -123,6 +123,10 @@ void adjacency(const double* d_S, int64_t n, double* d_A);
 void graph_components(const double* d_adj, int64_t n, int32_t* h_membership, int32_t* n_components);
 void graph_distances(const double* d_adj, int64_t n, double* d_D);
 
+// signaling.cu
+void signaling_pair(const double* d_lig, const double* d_rec, const double* d_beta, const double* d_gamma, int64_t n,
+                    bool normalize, double* d_P);
+
 // eigengap.cu
 void get_components(const double* d_S, int64_t n, double tol, double* h_vals, int32_t* n_eigs);
 void consensus_dense(const int32_t* d_labels, int R, int64_t n, double tau, double* d_consen);

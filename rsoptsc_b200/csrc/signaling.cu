@@ -1,0 +1,59 @@
+// Cell-cell signalling probability of one ligand-receptor pair:
+// the n^2 elementwise core of GetSignalingPartners (R/Signaling.R:187-309), i.e. updateFlatBoth /
+// updateFlatUp / updateFlatDown / updateFlatNone (:75-163) followed by the per-ligand-cell
+// normalisation (:291-293).  The reference evaluates the n^2 entries with foreach %dopar%.
+//   alpha_ij = exp(-1 / (L_i R_j))      (0 when L_i or R_j is 0)         getAlpha :24-30
+//   K = alpha / (alpha + beta_j), D = alpha / (alpha + gamma_j)  (0/0 := 0)   getK/getD :1-15
+//   both: alpha K D beta gamma | up: alpha K beta | down: alpha D gamma | none: alpha
+//   P[i, j] = value_ij / sum_j value_ij   (NaN -> 0)
+// HBM write-bound: 8 n^2 B out; the row sums are recomputed instead of stored (two exp passes).
+#include "internal.h"
+
+namespace rs {
+
+static constexpr int ST = 128;
+
+__device__ __forceinline__ double sig_value(double L, double R, double b, double g, int has_b, int has_g) {
+  const double a = (L == 0.0 || R == 0.0) ? 0.0 : exp(-1.0 / (L * R));
+  double v = a;
+  if (has_b) {
+    const double k = (a == 0.0 && b == 0.0) ? 0.0 : a / (a + b);
+    v = v * k;
+  }
+  if (has_g) {
+    const double d = (a == 0.0 && g == 0.0) ? 0.0 : a / (a + g);
+    v = v * d;
+  }
+  if (has_b) v = v * b;
+  if (has_g) v = v * g;
+  return v;
+}
+
+// one thread per ligand cell i; columns j walked in order so that stores are coalesced across i
+__global__ void k_signaling_pair(const double* __restrict__ lig, const double* __restrict__ rec,
+                                 const double* __restrict__ beta, const double* __restrict__ gamma, int64_t n,
+                                 int normalize, double* __restrict__ P) {
+  const int64_t i = (int64_t)blockIdx.x * ST + threadIdx.x;
+  if (i >= n) return;
+  const double L = lig[i];
+  const int hb = beta != nullptr, hg = gamma != nullptr;
+  double sum = 0;
+  if (normalize)
+    for (int64_t j = 0; j < n; ++j) sum += sig_value(L, rec[j], hb ? beta[j] : 0.0, hg ? gamma[j] : 0.0, hb, hg);
+  for (int64_t j = 0; j < n; ++j) {
+    double v = sig_value(L, rec[j], hb ? beta[j] : 0.0, hg ? gamma[j] : 0.0, hb, hg);
+    if (normalize) {
+      v = v / sum;
+      if (isnan(v)) v = 0.0;  // rows with zero total (R :293)
+    }
+    P[i + j * n] = v;
+  }
+}
+
+void signaling_pair(const double* d_lig, const double* d_rec, const double* d_beta, const double* d_gamma, int64_t n,
+                    bool normalize, double* d_P) {
+  Phase ph("signaling");
+  RS_LAUNCH(k_signaling_pair, (unsigned)cdiv(n, ST), ST, 0, d_lig, d_rec, d_beta, d_gamma, n, normalize ? 1 : 0, d_P);
+}
+
+}  // namespace rs

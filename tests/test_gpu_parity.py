@@ -282,6 +282,28 @@ def test_graph_distances_random(n):
     assert np.array_equal(np.isfinite(got), c["membership"][:, None] == c["membership"][None, :])
 
 
+# ---- GetSignalingPartners core ------------------------------------------------------
+def test_signaling_known_answer_and_oracle():
+    from test_oracle_golden import (SIGNAL_EXPR, SIGNAL_GENES, SIGNAL_LIGREC, SIGNAL_RECTARG, signal_known_answer)
+    got = api.GetSignalingPartners(SIGNAL_EXPR, SIGNAL_GENES, SIGNAL_LIGREC, SIGNAL_RECTARG)
+    ref = O.GetSignalingPartners(SIGNAL_EXPR, SIGNAL_GENES, SIGNAL_LIGREC, SIGNAL_RECTARG)
+    assert np.allclose(got["P"][0], signal_known_answer(), rtol=1e-13)      # tests/testthat/testSignal.R:16-81
+    for a, b in zip(got["P"], ref["P"]):
+        assert np.allclose(a, b, rtol=1e-13, atol=1e-300)
+    assert np.allclose(got["P_tot"], ref["P_tot"], rtol=1e-13)
+    # random expression with zeros (alpha = 0 branches, all-zero rows -> NaN -> 0), all four modes
+    rng = np.random.default_rng(5)
+    n = 150
+    lig = rng.poisson(1.0, n).astype(float)
+    rec = rng.poisson(1.5, n).astype(float)
+    beta = np.where(rng.random(n) < 0.2, 0.0, rng.random(n))
+    gamma = np.where(rng.random(n) < 0.2, 0.0, rng.random(n))
+    for b, g in [(beta, gamma), (beta, None), (None, gamma), (None, None)]:
+        for norm in (True, False):
+            assert np.allclose(api.signaling_pair(lig, rec, b, g, normalize=norm),
+                               O.signaling_pair(lig, rec, b, g, normalize=norm), rtol=1e-13, atol=1e-300)
+
+
 def test_similarity_forced_K_and_lambda():
     """config 5 forces K = 30; the vignette uses lambda = 0.05."""
     p = small_problem(200, 260, seed=31)

@@ -44,6 +44,40 @@ def test_computeM_known_answer(joost):
     assert np.count_nonzero(W) == 8622 and abs(W.sum() - 449.352) < 1e-3
 
 
+# inst/extdata/test_gene_expression.txt, test_ligrec.txt, test_rectarg_updown.txt (3 cells)
+SIGNAL_GENES = ["lig1", "lig2", "lig3", "rec1", "rec2", "targ_rec1_1", "targ_rec1_2", "targ_rec1_3", "targ_rec2_1"]
+SIGNAL_EXPR = np.array([[1, 2, 3], [1, 2, 1], [1, 0, 1], [2, 1, 2], [1, 3, 1], [0, 1, 0], [3, 3, 3], [8, 9, 8],
+                        [1, 4, 1]], dtype=np.float64)
+SIGNAL_LIGREC = [("lig1", "rec1"), ("lig2", "rec1"), ("lig2", "rec2"), ("lig3", "rec2")]
+SIGNAL_RECTARG = [("rec1", "targ_rec1_1", "up"), ("rec1", "targ_rec1_2", "up"), ("rec1", "targ_rec1_3", "down"),
+                  ("rec2", "targ_rec2_1", "down")]
+
+
+def signal_known_answer():
+    """The hand-computed pLig1Rec1 of tests/testthat/testSignal.R:26-74."""
+    e = np.exp
+    L = [1.0, 2.0, 3.0]          # lig1 in cells 1..3
+    R = [2.0, 1.0, 2.0]          # rec1
+    up = [e(-2 / 3), e(-2 / 4), e(-2 / 3)]
+    down = [e(-8 / 1), e(-9 / 1), e(-8 / 1)]
+    P = np.zeros((3, 3))
+    for i in range(3):
+        for j in range(3):
+            a = e(-1 / (L[i] * R[j]))
+            P[i, j] = a * (a / (a + up[j]) * up[j]) * (a / (a + down[j]) * down[j])
+    return P / P.sum(axis=1, keepdims=True)
+
+
+def test_signaling_known_answer():
+    # tests/testthat/testSignal.R:16-81
+    r = O.GetSignalingPartners(SIGNAL_EXPR, SIGNAL_GENES, SIGNAL_LIGREC, SIGNAL_RECTARG)
+    assert np.allclose(r["P"][0], signal_known_answer(), rtol=1e-12, atol=0)
+    for p in r["P"]:
+        sums = p.sum(axis=1)
+        assert np.all((np.abs(sums - 1) < 1e-12) | (sums == 0))
+    assert np.allclose(r["P_tot"].sum(axis=1), 1.0)
+
+
 def test_knn_self_included_and_mask():
     rng = np.random.default_rng(1)
     emb = rng.normal(size=(200, 3))
