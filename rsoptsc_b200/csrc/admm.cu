@@ -201,7 +201,7 @@ void run_admm(const double* d_X, int64_t m, int64_t n, const Support& s, double 
           const int64_t nc = s.comp_n[cidx];
           if (J) {
             const double minus1 = -1.0;
-            RS_CUBLAS(cublasDaxpy(c.cublas, (int)(nc * nc), &minus1, J + s.comp_off[cidx], 1, Dm.p + s.comp_off[cidx], 1));
+            RS_CUBLAS(cublasDaxpy_64(c.cublas, nc * nc, &minus1, J + s.comp_off[cidx], 1, Dm.p + s.comp_off[cidx], 1));
           }
           err2 = std::max(err2, spectral_norm(Dm.p + s.comp_off[cidx], nc, nc));
         }

@@ -38,23 +38,14 @@ __global__ void k_laplacian_block(const double* __restrict__ S, const double* __
 static void block_eigenvalues(double* d_L, int64_t nc, std::vector<double>& out) {
   Context& c = ctx();
   DevBuf<double> lam(nc);
-  int lwork = 0;
-  RS_CUSOLVER(cusolverDnDsyevd_bufferSize(c.cusolver, CUSOLVER_EIG_MODE_NOVECTOR, CUBLAS_FILL_MODE_LOWER, (int)nc, d_L,
-                                          (int)nc, lam.p, &lwork));
-  DevBuf<double> work((size_t)std::max(lwork, 1));
-  DevBuf<int> info(1);
   {
     Phase ph("eig");
-    RS_CUSOLVER(cusolverDnDsyevd(c.cusolver, CUSOLVER_EIG_MODE_NOVECTOR, CUBLAS_FILL_MODE_LOWER, (int)nc, d_L, (int)nc,
-                                 lam.p, work.p, lwork, info.p));
+    sym_eig(d_L, nc, lam.p, /*vectors=*/false);
   }
   const size_t at = out.size();
   out.resize(at + nc);
-  int hinfo = 0;
   RS_CUDA(cudaMemcpyAsync(out.data() + at, lam.p, sizeof(double) * nc, cudaMemcpyDeviceToHost, c.stream));
-  RS_CUDA(cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   RS_CUDA(cudaStreamSynchronize(c.stream));
-  RS_REQUIRE(hinfo == 0, "get_components: eigensolver failed");
 }
 
 // Spectrum of I - D^-1/2 S D^-1/2.  The Laplacian is block diagonal over the connected components
@@ -62,7 +53,6 @@ static void block_eigenvalues(double* d_L, int64_t nc, std::vector<double>& out)
 // eigensolver work instead of n^3).  The pattern is taken from the CSC view when S is sparse.
 static void laplacian_spectrum(const double* d_S, int64_t n, std::vector<double>& vals, const Compressed* csc_in = nullptr) {
   Context& c = ctx();
-  RS_REQUIRE(n <= 46340, "get_components: n too large for the dense eigensolver");
   RS_REQUIRE(n <= 65535, "get_components: n too large for this launch shape");
   DevBuf<double> ones(n), deg(n);
   RS_LAUNCH(k_fill_ones, (unsigned)cdiv(n, ET), ET, 0, ones.p, n);

@@ -85,11 +85,13 @@ double spectral_norm(const double* d_M, int64_t rows, int64_t cols, double rel_t
 void tridiag_eig(std::vector<double>& d, std::vector<double>& e, std::vector<double>* Zv, bool last_row_only = false);
 
 // ---- singular value thresholding (svt.cu) -------------------------------------------
+// eig.cu: dense symmetric eigensolver (lower triangle of A; eigenvectors overwrite A when requested,
+// eigenvalues ascending in d_lam)
+void sym_eig(double* d_A, int64_t n, double* d_lam, bool vectors);
+
 struct SvtWorkspace {
   int64_t n = 0;
-  DevBuf<double> G, T, lam, work;
-  DevBuf<int> info;
-  int lwork = 0;
+  DevBuf<double> G, T, lam;
   void ensure(int64_t n);
 };
 // J = SVT_tau(A) written over A.  Returns rank(J).

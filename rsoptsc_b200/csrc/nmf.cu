@@ -242,16 +242,9 @@ static void nndsvd_seed(const double* d_V, const Compressed& csr, const Compress
   } else {
     // dense eigen-decomposition of V^T V (the reference takes a full SVD of V anyway)
     RS_REQUIRE(n <= 8192, "nmf: repeated singular values need the dense NNDSVD path, limited to n <= 8192");
-    Context& c = ctx();
     DevBuf<double> G((size_t)n * n), lam(n);
     gram_AtA(d_V, n, n, G.p);
-    int lwork = 0;
-    RS_CUSOLVER(cusolverDnDsyevd_bufferSize(c.cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, G.p,
-                                            (int)n, lam.p, &lwork));
-    DevBuf<double> work((size_t)std::max(lwork, 1));
-    DevBuf<int> info(1);
-    RS_CUSOLVER(cusolverDnDsyevd(c.cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, G.p, (int)n,
-                                 lam.p, work.p, lwork, info.p));
+    sym_eig(G.p, n, lam.p, /*vectors=*/true);
     theta.assign(n, 0.0);
     RS_CUDA(cudaMemcpyAsync(theta.data(), lam.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
     for (int i = 0; i < k; ++i) {

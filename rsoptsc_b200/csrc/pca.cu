@@ -35,7 +35,7 @@ void pca_spectrum(const double* d_X, int64_t m, int64_t n, std::vector<double>& 
   Context& c = ctx();
   RS_REQUIRE(m >= 1 && n >= 2, "pca: need at least 2 cells");
   const int64_t d = std::min(m, n);
-  RS_REQUIRE(d <= 46340, "pca: min(m, n) too large for the dense eigensolver");
+  RS_REQUIRE(d <= 65535, "pca: min(m, n) too large for the dense eigensolver");
   RS_REQUIRE(ncomp >= 0 && ncomp <= d, "pca: ncomp out of range");
   // row means: X * (1/n)
   DevBuf<double> ones(n), mean(m), Xc((size_t)m * n);
@@ -47,19 +47,10 @@ void pca_spectrum(const double* d_X, int64_t m, int64_t n, std::vector<double>& 
   DevBuf<double> G((size_t)d * d), lam(d);
   const bool gene_side = m <= n;
   if (gene_side) gram_AAt(Xc.p, m, n, G.p); else gram_AtA(Xc.p, m, n, G.p);
-  int lwork = 0;
-  RS_CUSOLVER(cusolverDnDsyevd_bufferSize(c.cusolver, ncomp ? CUSOLVER_EIG_MODE_VECTOR : CUSOLVER_EIG_MODE_NOVECTOR,
-                                          CUBLAS_FILL_MODE_LOWER, (int)d, G.p, (int)d, lam.p, &lwork));
-  DevBuf<double> work((size_t)lwork);
-  DevBuf<int> info(1);
-  RS_CUSOLVER(cusolverDnDsyevd(c.cusolver, ncomp ? CUSOLVER_EIG_MODE_VECTOR : CUSOLVER_EIG_MODE_NOVECTOR,
-                               CUBLAS_FILL_MODE_LOWER, (int)d, G.p, (int)d, lam.p, work.p, lwork, info.p));
+  sym_eig(G.p, d, lam.p, /*vectors=*/ncomp > 0);
   std::vector<double> h(d);
-  int hinfo = 0;
   RS_CUDA(cudaMemcpyAsync(h.data(), lam.p, sizeof(double) * d, cudaMemcpyDeviceToHost, c.stream));
-  RS_CUDA(cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   RS_CUDA(cudaStreamSynchronize(c.stream));
-  RS_REQUIRE(hinfo == 0, "pca: eigensolver failed");
   eig.resize(d);
   const double denom = (double)std::max<int64_t>(1, n - 1);
   for (int64_t i = 0; i < d; ++i) eig[i] = std::max(h[d - 1 - i], 0.0) / denom;  // descending sdev^2

@@ -6,11 +6,12 @@
 // i.e. one syrk-shaped contraction, one symmetric eigen-decomposition and two GEMMs whose inner
 // dimension shrinks with the rank of J.  In FP64 this matches the SVD route to ~1e-15 relative
 // in Z (scratch/proto_admm.py); FP32-level Gram accuracy does NOT (7e-7), because squaring
-// buries singular values below sqrt(eps)*sigma_1 -- hence the FP64(-equivalent) requirement.
+// buries singular values below sqrt(eps)*sigma_1 -- hence the FP64(-equivalent) requirement, met
+// on the tensor cores by the split-integer GEMM of gemm_ozaki.cu.
 #include <cmath>
 
-#include "internal.h"
 #include "gemm.h"
+#include "internal.h"
 
 namespace rs {
 
@@ -20,14 +21,10 @@ void SvtWorkspace::ensure(int64_t n_) {
   G.alloc((size_t)n * n);
   T.alloc((size_t)n * n);
   lam.alloc(n);
-  info.alloc(1);
-  RS_CUSOLVER(cusolverDnDsyevd_bufferSize(ctx().cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, G.p,
-                                          (int)n, lam.p, &lwork));
-  work.alloc((size_t)lwork);
 }
 
 int64_t svt_inplace(SvtWorkspace& ws, double* d_A, int64_t n, double tau) {
-  RS_REQUIRE(n <= 46340, "svt: n too large for the 32-bit dense solver interface");
+  RS_REQUIRE(n <= 65535, "svt: block larger than 65,535 cells");
   ws.ensure(n);
   Context& c = ctx();
   {  // G = A^T A (lower triangle)
@@ -36,15 +33,11 @@ int64_t svt_inplace(SvtWorkspace& ws, double* d_A, int64_t n, double tau) {
   }
   {  // G -> V (columns), lam ascending
     Phase ph("eig");
-    RS_CUSOLVER(cusolverDnDsyevd(c.cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, ws.G.p, (int)n,
-                                 ws.lam.p, ws.work.p, ws.lwork, ws.info.p));
+    sym_eig(ws.G.p, n, ws.lam.p, /*vectors=*/true);
   }
   std::vector<double> lam(n);
-  int info = 0;
   RS_CUDA(cudaMemcpyAsync(lam.data(), ws.lam.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
-  RS_CUDA(cudaMemcpyAsync(&info, ws.info.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   RS_CUDA(cudaStreamSynchronize(c.stream));
-  RS_REQUIRE(info == 0, "svt: symmetric eigensolver did not converge (info=" + std::to_string(info) + ")");
   // shrink factors; eigenvalues ascending so the kept ones are a suffix
   std::vector<double> h(n, 0.0);
   int64_t r0 = n;
