@@ -143,7 +143,47 @@ SEXP rsoptsc_R_count_clusters(SEXP S, SEXP tol, SEXP lo, SEXP hi, SEXP n_comp) {
   return out;
 }
 
+/* .Call("rsoptsc_R_graph_distances", adj) -> n x n unweighted shortest-path lengths (Inf if unreachable);
+ * replaces igraph::distances(similarity_graph) in RepresentationMap (R/RepresentationMap.R:89) */
+SEXP rsoptsc_R_graph_distances(SEXP adj) {
+  int64_t n, nc;
+  dims(adj, &n, &nc);
+  if (n != nc) Rf_error("adjacency matrix must be square");
+  SEXP D = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)n));
+  int st = rsoptsc_graph_distances(REAL(adj), n, REAL(D));
+  if (st != 0) { UNPROTECT(1); check(st); }
+  UNPROTECT(1);
+  return D;
+}
+
+/* .Call("rsoptsc_R_dist_flat", flat_embedding) -> as.matrix(dist(flat_embedding)) (R/RepresentationMap.R:57) */
+SEXP rsoptsc_R_dist_flat(SEXP emb) {
+  int64_t n, d;
+  dims(emb, &n, &d);
+  SEXP D = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)n));
+  int st = rsoptsc_dist_flat(REAL(emb), n, (int32_t)d, REAL(D));
+  if (st != 0) { UNPROTECT(1); check(st); }
+  UNPROTECT(1);
+  return D;
+}
+
+/* .Call("rsoptsc_R_signaling_pair", lig, rec, beta_or_NULL, gamma_or_NULL) -> row-normalised n x n P
+ * (updateFlat* + normalisation of GetSignalingPartners, R/Signaling.R:75-163, :291-293) */
+SEXP rsoptsc_R_signaling_pair(SEXP lig, SEXP rec, SEXP beta, SEXP gamma) {
+  const R_xlen_t n = Rf_xlength(lig);
+  if (Rf_xlength(rec) != n) Rf_error("lig and rec must have one value per cell");
+  SEXP P = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)n));
+  int st = rsoptsc_signaling_pair(REAL(lig), REAL(rec), Rf_isNull(beta) ? NULL : REAL(beta),
+                                  Rf_isNull(gamma) ? NULL : REAL(gamma), (int64_t)n, 1, REAL(P));
+  if (st != 0) { UNPROTECT(1); check(st); }
+  UNPROTECT(1);
+  return P;
+}
+
 static const R_CallMethodDef call_methods[] = {
+    {"rsoptsc_R_graph_distances", (DL_FUNC)&rsoptsc_R_graph_distances, 1},
+    {"rsoptsc_R_dist_flat", (DL_FUNC)&rsoptsc_R_dist_flat, 1},
+    {"rsoptsc_R_signaling_pair", (DL_FUNC)&rsoptsc_R_signaling_pair, 4},
     {"rsoptsc_R_similarity", (DL_FUNC)&rsoptsc_R_similarity, 4},
     {"rsoptsc_R_computeM", (DL_FUNC)&rsoptsc_R_computeM, 3},
     {"rsoptsc_R_nmf", (DL_FUNC)&rsoptsc_R_nmf, 2},

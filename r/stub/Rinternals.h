@@ -25,6 +25,7 @@ SEXP Rf_ScalarReal(double x);
 SEXP Rf_ScalarInteger(int x);
 void SET_VECTOR_ELT(SEXP x, R_xlen_t i, SEXP v);
 void SET_STRING_ELT(SEXP x, R_xlen_t i, SEXP v);
+R_xlen_t Rf_xlength(SEXP x);
 int Rf_isNull(SEXP x);
 int Rf_isReal(SEXP x);
 int Rf_isInteger(SEXP x);

@@ -12,6 +12,9 @@ namespace rs {
 void sym_eig(double* d_A, int64_t n, double* d_lam, bool vectors) {
   Context& c = ctx();
   RS_REQUIRE(n >= 1, "sym_eig: empty matrix");
+  // probed on B200 / CUDA 12.9 (scratch/eig_limit_probe.cu): Xsyevd_bufferSize returns INVALID_VALUE above 32,768
+  RS_REQUIRE(n <= 32768, "symmetric eigensolver: a connected block of " + std::to_string(n) +
+                             " cells exceeds cuSOLVER's 32,768-row limit (largest supported dense block)");
   static cusolverDnParams_t params = nullptr;
   if (!params) RS_CUSOLVER(cusolverDnCreateParams(&params));
   const cusolverEigMode_t mode = vectors ? CUSOLVER_EIG_MODE_VECTOR : CUSOLVER_EIG_MODE_NOVECTOR;
