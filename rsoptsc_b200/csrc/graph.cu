@@ -35,16 +35,19 @@ void dist_flat(const double* d_emb, int64_t n, int dim, double* d_D) {
 }
 
 // ---- adjacency -------------------------------------------------------------------------------------
+// HBM-bound: 8 n^2 B in, 8 n^2 B out; one column per blockIdx.y (no 64-bit div/mod per element)
 __global__ void k_adjacency(const double* __restrict__ S, int64_t n, double* __restrict__ A) {
-  const int64_t total = n * n;
-  for (int64_t e = (int64_t)blockIdx.x * GT + threadIdx.x; e < total; e += (int64_t)gridDim.x * GT) {
-    const int64_t i = e % n, j = e / n;
-    A[e] = (S[e] > 0.0 && i != j) ? 1.0 : 0.0;
-  }
+  const int64_t j = blockIdx.y;
+  const double* src = S + j * n;
+  double* dst = A + j * n;
+  for (int64_t i = (int64_t)blockIdx.x * GT + threadIdx.x; i < n; i += (int64_t)gridDim.x * GT)
+    dst[i] = (src[i] > 0.0 && i != j) ? 1.0 : 0.0;
 }
 void adjacency(const double* d_S, int64_t n, double* d_A) {
   Phase ph("adjacency");
-  RS_LAUNCH(k_adjacency, 148 * 8, GT, 0, d_S, n, d_A);
+  RS_REQUIRE(n <= 65535, "adjacency: n too large for this launch shape");
+  dim3 grid((unsigned)std::min<int64_t>(cdiv(n, GT), 8), (unsigned)n);
+  RS_LAUNCH(k_adjacency, grid, GT, 0, d_S, n, d_A);
 }
 
 // ---- undirected neighbour lists from a dense adjacency: edge {i,j} if adj[i,j] != 0 or adj[j,i] != 0
