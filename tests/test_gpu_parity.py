@@ -336,6 +336,21 @@ def test_error_paths_return_status_not_crash():
     assert np.allclose(api.normalize(np.arange(12.0).reshape(3, 4) + 1).sum(), api.normalize(np.arange(12.0).reshape(3, 4) + 1).sum())
 
 
+def test_nmf_max_iter_cap_and_reinit(joost):
+    """maxIter not a multiple of the stop-check interval (graph replay + tail iterations), then a
+    finalize / re-init cycle of the library."""
+    from rsoptsc_b200 import _lib
+    ref = O.nmf_lee(joost["S"], 9, max_iter=25)
+    got = api.nmf_lee(joost["S"], 9, max_iter=25)
+    assert got["iters"] == ref["iters"] == 25
+    assert relF(got["W"], ref["W"]) < 1e-10
+    lib = _lib.load()
+    assert lib.rsoptsc_finalize() == 0
+    assert lib.rsoptsc_init(0) == 0
+    again = api.nmf_lee(joost["S"], 9, max_iter=25)
+    assert np.array_equal(again["W"], got["W"])
+
+
 def test_repeated_calls_are_deterministic():
     """Caching allocator / persistent workspaces: same inputs -> bit-identical outputs, run to run."""
     p = small_problem(120, 300, seed=8)
