@@ -15,15 +15,23 @@ static constexpr int RED_THREADS = 256;
 struct RedScratch {
   DevBuf<double> partial, result;
   void ensure() {
-    if (!partial.p) { partial.alloc(RED_BLOCKS * 2); result.alloc(2); }
+    if (!partial.p) partial.alloc(RED_BLOCKS * 2);
+    if (!result.p) result.alloc(2);
   }
 };
-static RedScratch& red() {
+static RedScratch& red_storage() {
   static RedScratch r;
+  return r;
+}
+static RedScratch& red() {
+  RedScratch& r = red_storage();
   r.ensure();
   return r;
 }
-void release_dense_scratch() { red().partial.release(); red().result.release(); }
+void release_dense_scratch() {  // rsoptsc_finalize / device switch: hand the scratch back without re-creating it
+  red_storage().partial.release();
+  red_storage().result.release();
+}
 
 __global__ void k_final_sum(const double* __restrict__ partial, int count, double* __restrict__ out) {
   __shared__ double sm[RED_THREADS / 32 + 1];
