@@ -156,6 +156,22 @@ int rsoptsc_graph_components(const double* adj, int64_t n, int32_t* membership,
 /* igraph::distances(graph) (:89): all-pairs unweighted shortest path lengths, Inf if unreachable */
 int rsoptsc_graph_distances(const double* adj, int64_t n, double* dist);
 
+/* ---- preprocessing upstream of the path (R/DataSelection.R) ---- */
+/* LogNormalize(M, scale, normalize) :117-133  (M, out: genes x cells) */
+int rsoptsc_log_normalize(const double* M, int64_t m, int64_t n, double scale, int32_t normalize,
+                          double* out);
+/* ScaleCenterData(M) :63-76  per-gene z-score, sd == 0 -> 1 */
+int rsoptsc_scale_center(const double* M, int64_t m, int64_t n, double* out);
+/* ApplyCountThreshold(M, countL, countU, X) :91-103: keep[g] = 1 for genes to keep (the R function
+ * returns which(keep)) */
+int rsoptsc_count_threshold(const double* M, int64_t m, int64_t n, double countL, double countU,
+                            double X, int32_t* keep);
+/* SelectData(M, gene_expression_threshold, n_features) :17-51: gene_use (0-based rows of M, capacity
+ * m), *n_selected their count, *max_component (may be NULL) the number of PCs used */
+int rsoptsc_select_data(const double* M, int64_t m, int64_t n, double gene_expression_threshold,
+                        int32_t n_features, int32_t* gene_use, int32_t* n_selected,
+                        int32_t* max_component);
+
 /* ---- GetSignalingPartners core (R/Signaling.R:75-163,291-293) ---- */
 /* P[i,j] (n x n, i = ligand cell, j = receptor cell) for one ligand-receptor pair: lig, rec = the
  * two expression rows (n); beta / gamma = per-cell up / down target terms (getBetaj / getGammaj),

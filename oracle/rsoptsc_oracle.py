@@ -432,6 +432,63 @@ def graph_components(adj):
 
 
 # --------------------------------------------------------------------------------------
+# Preprocessing upstream of the path  (R/DataSelection.R) -- parity unpinned (no reference test)
+# --------------------------------------------------------------------------------------
+def LogNormalize(M, scale=1e4, normalize=True):
+    """R/DataSelection.R:117-133."""
+    M = np.asarray(M, dtype=np.float64)
+    MM = M.copy()
+    if normalize:
+        mx = M.max(axis=0)
+        pos = mx > 0
+        MM[:, pos] = M[:, pos] / mx[pos]
+    return np.log10(scale * MM + 1.0)
+
+
+def ScaleCenterData(M):
+    """R/DataSelection.R:63-76 (sd = sample standard deviation; 0 -> 1)."""
+    M = np.asarray(M, dtype=np.float64)
+    means = M.mean(axis=1, keepdims=True)
+    sds = M.std(axis=1, ddof=1, keepdims=True)
+    sds[sds == 0] = 1.0
+    return (M - means) / sds
+
+
+def ApplyCountThreshold(M, countL=1, countU=3, X=3):
+    """R/DataSelection.R:91-103 -> 1-based kept gene indices."""
+    M = np.asarray(M)
+    n = M.shape[1]
+    upper = ~(((M >= countU).sum(axis=1) / n) >= (100 - X) * 0.01)
+    lower = ((M >= countL).sum(axis=1) / n) >= X * 0.01
+    return np.flatnonzero(upper & lower) + 1
+
+
+def SelectData(M, gene_expression_threshold, n_features):
+    """R/DataSelection.R:17-51 -> dict(gene_use 1-based, M_variable, max_component)."""
+    M = np.asarray(M, dtype=np.float64)
+    m, n = M.shape
+    if gene_expression_threshold > 0:                                       # :22-30
+        alpha = gene_expression_threshold / n
+        nnz = (M != 0).sum(axis=1) / n
+        gene_use = np.flatnonzero((nnz > alpha) & (nnz < 1 - alpha))
+    else:
+        gene_use = np.arange(m)
+    Mv = M[gene_use]
+    T = Mv.T                                                                # prcomp(t(M_variable)) :33
+    Tc = T - T.mean(axis=0, keepdims=True)
+    _, d, Vt = sla.svd(Tc, full_matrices=False, lapack_driver="gesdd")
+    sdev = d / np.sqrt(max(1, n - 1))
+    eigengaps = np.abs(sdev[1:-1] - sdev[2:])                               # :34
+    max_component = int(np.flatnonzero(eigengaps == eigengaps.max())[0]) + 1 + 1   # :35 (1-based which + 1)
+    rot = Vt.T                                                              # genes x components, sdev already descending
+    max_coeffs = np.abs(rot[:, :max_component]).max(axis=1)                 # :39-41
+    adj_n = min(Mv.shape[0], n_features)                                    # :45
+    nth = np.sort(max_coeffs)[::-1][adj_n - 1]
+    idx = np.flatnonzero(max_coeffs >= nth)                                 # :47
+    return dict(gene_use=gene_use[idx] + 1, M_variable=Mv[idx], max_component=max_component)
+
+
+# --------------------------------------------------------------------------------------
 # GetSignalingPartners  (R/Signaling.R:1-60, 75-163, 187-309) -- pinned by the hand-computed
 # known answer of tests/testthat/testSignal.R:16-81 (tests/test_oracle_golden.py)
 # --------------------------------------------------------------------------------------

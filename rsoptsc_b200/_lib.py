@@ -61,6 +61,12 @@ SIGNATURES = {
     "rsoptsc_adjacency": (C.c_int, [c_double_p, C.c_int64, c_double_p]),
     "rsoptsc_graph_components": (C.c_int, [c_double_p, C.c_int64, c_int32_p, c_int32_p]),
     "rsoptsc_graph_distances": (C.c_int, [c_double_p, C.c_int64, c_double_p]),
+    "rsoptsc_log_normalize": (C.c_int, [c_double_p, C.c_int64, C.c_int64, C.c_double, C.c_int32, c_double_p]),
+    "rsoptsc_scale_center": (C.c_int, [c_double_p, C.c_int64, C.c_int64, c_double_p]),
+    "rsoptsc_count_threshold": (C.c_int, [c_double_p, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double,
+                                          c_int32_p]),
+    "rsoptsc_select_data": (C.c_int, [c_double_p, C.c_int64, C.c_int64, C.c_double, C.c_int32, c_int32_p, c_int32_p,
+                                      c_int32_p]),
     "rsoptsc_signaling_pair": (C.c_int, [c_double_p, c_double_p, c_double_p, c_double_p, C.c_int64, C.c_int32,
                                          c_double_p]),
     "rsoptsc_set_gemm_backend": (C.c_int, [C.c_int32]),

@@ -261,6 +261,49 @@ def RepresentationMap(flat_embedding, similarity_matrix, join_components=False, 
                 dist_graph=graph_distances(adj), flat_embedding=flat_embedding)
 
 
+def LogNormalize(M, scale=1e4, normalize=True):
+    """R/DataSelection.R:117-133."""
+    lib = _lib.init()
+    a = _f64(M)
+    m, n = a.shape
+    out = np.empty((m, n), dtype=np.float64, order="F")
+    _lib.check(lib.rsoptsc_log_normalize(_dp(a), m, n, float(scale), 1 if normalize else 0, _dp(out)))
+    return out
+
+
+def ScaleCenterData(M):
+    """R/DataSelection.R:63-76."""
+    lib = _lib.init()
+    a = _f64(M)
+    m, n = a.shape
+    out = np.empty((m, n), dtype=np.float64, order="F")
+    _lib.check(lib.rsoptsc_scale_center(_dp(a), m, n, _dp(out)))
+    return out
+
+
+def ApplyCountThreshold(M, countL=1, countU=3, X=3):
+    """R/DataSelection.R:91-103 -> 1-based indices of the genes to keep (like which())."""
+    lib = _lib.init()
+    a = _f64(M)
+    m, n = a.shape
+    keep = np.zeros(m, dtype=np.int32)
+    _lib.check(lib.rsoptsc_count_threshold(_dp(a), m, n, float(countL), float(countU), float(X), _ip(keep)))
+    return np.flatnonzero(keep) + 1
+
+
+def SelectData(M, gene_expression_threshold, n_features):
+    """R/DataSelection.R:17-51 -> dict(gene_use 1-based, M_variable, max_component)."""
+    lib = _lib.init()
+    a = _f64(M)
+    m, n = a.shape
+    use = np.zeros(m, dtype=np.int32)
+    cnt, mc = C.c_int32(0), C.c_int32(0)
+    _lib.check(lib.rsoptsc_select_data(_dp(a), m, n, float(gene_expression_threshold), int(n_features), _ip(use),
+                                       C.byref(cnt), C.byref(mc)))
+    sel = use[:cnt.value].astype(np.int64)
+    return dict(gene_use=sel + 1, M_variable=a[sel, :], max_component=int(mc.value))
+
+
 def signaling_pair(lig, rec, beta=None, gamma=None, normalize=True):
     """P (n x n) of one ligand-receptor pair: updateFlat{Both,Up,Down,None} + row normalisation
     (R/Signaling.R:75-163, :291-293)."""

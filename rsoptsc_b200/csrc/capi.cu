@@ -583,6 +583,61 @@ int rsoptsc_graph_distances(const double* adj, int64_t n, double* dist) {
   });
 }
 
+// ---- preprocessing (R/DataSelection.R) -------------------------------------------------------
+int rsoptsc_log_normalize(const double* M, int64_t m, int64_t n, double scale, int32_t normalize, double* out) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(m > 0 && n > 0, "log_normalize: empty matrix");
+    DevBuf<double> a((size_t)m * n), o((size_t)m * n);
+    a.upload(M, (size_t)m * n, s);
+    log_normalize(a.p, m, n, scale, normalize != 0, o.p);
+    o.download(out, (size_t)m * n, s);
+    RS_CUDA(cudaStreamSynchronize(s));
+  });
+}
+int rsoptsc_scale_center(const double* M, int64_t m, int64_t n, double* out) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(m > 0 && n > 0, "scale_center: empty matrix");
+    DevBuf<double> a((size_t)m * n), o((size_t)m * n);
+    a.upload(M, (size_t)m * n, s);
+    scale_center(a.p, m, n, o.p);
+    o.download(out, (size_t)m * n, s);
+    RS_CUDA(cudaStreamSynchronize(s));
+  });
+}
+int rsoptsc_count_threshold(const double* M, int64_t m, int64_t n, double countL, double countU, double X,
+                            int32_t* keep) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(m > 0 && n > 0, "count_threshold: empty matrix");
+    DevBuf<double> a((size_t)m * n);
+    a.upload(M, (size_t)m * n, s);
+    std::vector<double> st;
+    gene_stats(a.p, m, n, countL, countU, st);
+    for (int64_t g = 0; g < m; ++g) {                       // R/DataSelection.R:94-102
+      const bool upper = !((st[4 * m + g] / (double)n) >= (100.0 - X) * 0.01);
+      const bool lower = (st[3 * m + g] / (double)n) >= X * 0.01;
+      keep[g] = (upper && lower) ? 1 : 0;
+    }
+  });
+}
+int rsoptsc_select_data(const double* M, int64_t m, int64_t n, double gene_expression_threshold, int32_t n_features,
+                        int32_t* gene_use, int32_t* n_selected, int32_t* max_component) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(m > 0 && n > 0, "select_data: empty matrix");
+    DevBuf<double> a((size_t)m * n);
+    a.upload(M, (size_t)m * n, s);
+    std::vector<int> sel;
+    int mc = 0;
+    select_data(a.p, m, n, gene_expression_threshold, n_features, sel, &mc);
+    for (size_t i = 0; i < sel.size(); ++i) gene_use[i] = sel[i];
+    if (n_selected) *n_selected = (int32_t)sel.size();
+    if (max_component) *max_component = mc;
+  });
+}
+
 int rsoptsc_signaling_pair(const double* lig, const double* rec, const double* beta, const double* gamma, int64_t n,
                            int32_t normalize, double* P) {
   return guarded([&] {

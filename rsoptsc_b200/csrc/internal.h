@@ -113,6 +113,14 @@ void knn_bruteforce(const double* d_emb, int64_t n, int64_t ld, int dim, int K, 
 void pca_spectrum(const double* d_X, int64_t m, int64_t n, std::vector<double>& eig, double* d_emb,
                   int ncomp);
 int choose_K(const std::vector<double>& eig);
+void pca_loadings(const double* d_X, int64_t m, int64_t n, int ncomp, double* d_load /* m x ncomp */);
+
+// preprocess.cu (R/DataSelection.R)
+void log_normalize(const double* d_M, int64_t m, int64_t n, double scale, bool normalize, double* d_out);
+void scale_center(const double* d_M, int64_t m, int64_t n, double* d_out);
+void gene_stats(const double* d_M, int64_t m, int64_t n, double countL, double countU, std::vector<double>& h);
+void select_data(const double* d_M, int64_t m, int64_t n, double gene_expression_threshold, int n_features,
+                 std::vector<int>& selected, int* max_component_out);
 
 // nmf.cu
 struct NmfResult { int iters = 0; };

@@ -71,6 +71,46 @@ void pca_spectrum(const double* d_X, int64_t m, int64_t n, std::vector<double>& 
   }
 }
 
+// prcomp(t(X))$rotation[, 1:ncomp]: gene loadings (m x ncomp) of the leading principal components
+// (used by SelectData, R/DataSelection.R:33-41).  Signs are arbitrary (the caller takes abs()).
+void pca_loadings(const double* d_X, int64_t m, int64_t n, int ncomp, double* d_load) {
+  Phase ph("pca");
+  Context& c = ctx();
+  const int64_t d = std::min(m, n);
+  RS_REQUIRE(d <= 32768 && ncomp >= 1 && ncomp <= d, "pca_loadings: bad shape");
+  DevBuf<double> ones(n), mean(m), Xc((size_t)m * n);
+  RS_LAUNCH(k_fill, (unsigned)cdiv(n, 256), 256, 0, ones.p, n, 1.0 / (double)n);
+  DenseMatvec mv;
+  mv.init(d_X, m, n);
+  mv.mul_n(ones.p, mean.p);
+  RS_LAUNCH(k_center_rows, 148 * 8, 256, 0, d_X, m, n, mean.p, Xc.p);
+  DevBuf<double> G((size_t)d * d), lam(d);
+  const bool gene_side = m <= n;
+  if (gene_side) gram_AAt(Xc.p, m, n, G.p); else gram_AtA(Xc.p, m, n, G.p);
+  sym_eig(G.p, d, lam.p, true);
+  if (gene_side) {  // eigenvectors of Xc Xc^T are the loadings; leading ones are the last columns
+    for (int cidx = 0; cidx < ncomp; ++cidx)
+      RS_CUDA(cudaMemcpyAsync(d_load + (size_t)cidx * m, G.p + (size_t)(d - 1 - cidx) * d, sizeof(double) * m,
+                              cudaMemcpyDeviceToDevice, c.stream));
+  } else {          // loadings = Xc v / sigma for the cell-side eigenvectors v
+    std::vector<double> h(d);
+    RS_CUDA(cudaMemcpyAsync(h.data(), lam.p, sizeof(double) * d, cudaMemcpyDeviceToHost, c.stream));
+    RS_CUDA(cudaStreamSynchronize(c.stream));
+    DevBuf<double> Vtop((size_t)n * ncomp), sc(ncomp);
+    std::vector<double> hs(ncomp);
+    for (int cidx = 0; cidx < ncomp; ++cidx) {
+      RS_CUDA(cudaMemcpyAsync(Vtop.p + (size_t)cidx * n, G.p + (size_t)(d - 1 - cidx) * d, sizeof(double) * n,
+                              cudaMemcpyDeviceToDevice, c.stream));
+      const double l = std::max(h[d - 1 - cidx], 0.0);
+      hs[cidx] = l > 0 ? 1.0 / std::sqrt(l) : 0.0;
+    }
+    sc.upload(hs.data(), ncomp, c.stream);
+    gemm_nn(Xc.p, Vtop.p, d_load, m, ncomp, n);
+    scale_columns(d_load, m, ncomp, sc.p);
+  }
+  RS_CUDA(cudaStreamSynchronize(c.stream));
+}
+
 int choose_K(const std::vector<double>& eig) {
   // R/SimilarityM.R:61-72: cc = cumsum(eig[-1]); dd = cc[-1] / sum(eig[-1]); K1 = #{dd <= 0.3}
   const size_t L = eig.size();

@@ -282,6 +282,30 @@ def test_graph_distances_random(n):
     assert np.array_equal(np.isfinite(got), c["membership"][:, None] == c["membership"][None, :])
 
 
+# ---- preprocessing upstream of the path ---------------------------------------------
+def test_preprocessing_matches_oracle():
+    rng = np.random.default_rng(12)
+    m, n = 700, 180
+    counts = rng.poisson(rng.gamma(0.3, 2.0, size=(m, 1)), size=(m, n)).astype(float)
+    counts[:5] = 0                      # never-expressed genes
+    counts[5:8] = 7                     # constant genes (sd == 0)
+    counts[:, 3] = 0                    # an empty cell (max == 0 branch of LogNormalize)
+    assert np.allclose(api.LogNormalize(counts), O.LogNormalize(counts), rtol=1e-14, atol=0)
+    assert np.allclose(api.LogNormalize(counts, normalize=False), O.LogNormalize(counts, normalize=False), rtol=1e-14)
+    assert np.allclose(api.ScaleCenterData(counts), O.ScaleCenterData(counts), rtol=1e-12, atol=1e-13)
+    assert np.array_equal(api.ApplyCountThreshold(counts, 1, 3, 3), O.ApplyCountThreshold(counts, 1, 3, 3))
+    for thr, nf in [(3, 100), (0, 50), (10, 5000)]:
+        got = api.SelectData(counts, thr, nf)
+        ref = O.SelectData(counts, thr, nf)
+        assert got["max_component"] == ref["max_component"]
+        assert np.array_equal(got["gene_use"], ref["gene_use"])
+        assert np.array_equal(got["M_variable"], ref["M_variable"])
+    # cells > genes exercises the gene-side Gram branch of the loadings
+    small = counts[8:60]
+    got, ref = api.SelectData(small, 0, 10), O.SelectData(small, 0, 10)
+    assert got["max_component"] == ref["max_component"] and np.array_equal(got["gene_use"], ref["gene_use"])
+
+
 # ---- GetSignalingPartners core ------------------------------------------------------
 def test_signaling_known_answer_and_oracle():
     from test_oracle_golden import (SIGNAL_EXPR, SIGNAL_GENES, SIGNAL_LIGREC, SIGNAL_RECTARG, signal_known_answer)
