@@ -1,20 +1,79 @@
 // Dense symmetric eigensolver used by the SVT (a4), the PCA spectrum (a2) and the Laplacian
-// spectrum (a14): cuSOLVER's 64-bit API (cusolverDnXsyevd).  This is the one library call that
-// dominates the path; it is isolated here so that a native two-stage solver can
-// replace it.  The 64-bit entry point removes the int overflow of the legacy workspace size for
-// blocks above ~23,000 rows.
+// spectrum (a14).  This is the one library call that dominates the path; it
+// is isolated here so that a native two-stage solver can replace it.
+//   n <= 32,768 : cusolverDnXsyevd (64-bit API; the legacy entry point overflows its int workspace
+//                 size above ~23,000 rows)
+//   n  > 32,768 : cusolverDnXsyevd rejects the size (probed in scratch/eig_limit_probe.cu), so the
+//                 block goes through cusolverMgSyevd on this process's device (probed in
+//                 scratch/mg_probe.cu: 33,000 rows in 36.8 s on one B200)
+#include <cusolverMg.h>
+
 #include "internal.h"
 
 namespace rs {
+
+static int64_t mg_threshold() {
+  static int64_t t = -1;
+  if (t < 0) {
+    const char* e = getenv("RSOPTSC_MG_MIN_N");  // tests lower it to exercise the large-block path
+    t = e ? atoll(e) : 32768;
+    if (t < 1) t = 1;
+    if (t > 32768) t = 32768;
+  }
+  return t;
+}
+
+static void sym_eig_mg(double* d_A, int64_t n, double* d_lam, bool vectors) {
+  Context& c = ctx();
+  RS_REQUIRE(n <= 2147483647LL / 2, "sym_eig: block too large");
+  static cusolverMgHandle_t handle = nullptr;
+  static int handle_dev = -1;
+  if (!handle || handle_dev != c.device) {
+    if (handle) cusolverMgDestroy(handle);
+    RS_CUSOLVER(cusolverMgCreate(&handle));
+    int dev = c.device;
+    RS_CUSOLVER(cusolverMgDeviceSelect(handle, 1, &dev));
+    handle_dev = c.device;
+  }
+  const int64_t TB = 256;
+  const int64_t cols_pad = (n + TB - 1) / TB * TB;  // the 1-D block-cyclic layout owns whole column tiles
+  int32_t dev32 = c.device;
+  cudaLibMgGrid_t grid;
+  RS_CUSOLVER(cusolverMgCreateDeviceGrid(&grid, 1, 1, &dev32, CUDALIBMG_GRID_MAPPING_COL_MAJOR));
+  cudaLibMgMatrixDesc_t desc;
+  RS_CUSOLVER(cusolverMgCreateMatrixDesc(&desc, n, n, n, TB, CUDA_R_64F, grid));
+  DevBuf<double> Ap((size_t)n * cols_pad);
+  RS_CUDA(cudaMemcpyAsync(Ap.p, d_A, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, c.stream));
+  if (cols_pad > n)
+    RS_CUDA(cudaMemsetAsync(Ap.p + (size_t)n * n, 0, sizeof(double) * n * (cols_pad - n), c.stream));
+  RS_CUDA(cudaStreamSynchronize(c.stream));
+  void* arr_A[1] = {Ap.p};
+  std::vector<double> W(n);
+  const cusolverEigMode_t mode = vectors ? CUSOLVER_EIG_MODE_VECTOR : CUSOLVER_EIG_MODE_NOVECTOR;
+  int64_t lwork = 0;
+  RS_CUSOLVER(cusolverMgSyevd_bufferSize(handle, mode, CUBLAS_FILL_MODE_LOWER, (int)n, arr_A, 1, 1, desc, W.data(),
+                                         CUDA_R_64F, CUDA_R_64F, &lwork));
+  DevBuf<double> work((size_t)std::max<int64_t>(lwork, 1));
+  void* arr_W[1] = {work.p};
+  int info = 0;
+  cusolverStatus_t st = cusolverMgSyevd(handle, mode, CUBLAS_FILL_MODE_LOWER, (int)n, arr_A, 1, 1, desc, W.data(),
+                                        CUDA_R_64F, CUDA_R_64F, arr_W, lwork, &info);
+  RS_CUDA(cudaDeviceSynchronize());
+  cusolverMgDestroyMatrixDesc(desc);
+  cusolverMgDestroyGrid(grid);
+  RS_CUSOLVER(st);
+  RS_REQUIRE(info == 0, "symmetric eigensolver (Mg) did not converge (info=" + std::to_string(info) + ")");
+  if (vectors) RS_CUDA(cudaMemcpyAsync(d_A, Ap.p, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, c.stream));
+  RS_CUDA(cudaMemcpyAsync(d_lam, W.data(), sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+  RS_CUDA(cudaStreamSynchronize(c.stream));
+}
 
 // A (n x n, lower triangle referenced) -> eigenvectors in A (when `vectors`), eigenvalues ascending
 // in d_lam.  Throws when the solver reports failure.
 void sym_eig(double* d_A, int64_t n, double* d_lam, bool vectors) {
   Context& c = ctx();
   RS_REQUIRE(n >= 1, "sym_eig: empty matrix");
-  // probed on B200 / CUDA 12.9 (scratch/eig_limit_probe.cu): Xsyevd_bufferSize returns INVALID_VALUE above 32,768
-  RS_REQUIRE(n <= 32768, "symmetric eigensolver: a connected block of " + std::to_string(n) +
-                             " cells exceeds cuSOLVER's 32,768-row limit (largest supported dense block)");
+  if (n > mg_threshold()) return sym_eig_mg(d_A, n, d_lam, vectors);
   static cusolverDnParams_t params = nullptr;
   if (!params) RS_CUSOLVER(cusolverDnCreateParams(&params));
   const cusolverEigMode_t mode = vectors ? CUSOLVER_EIG_MODE_VECTOR : CUSOLVER_EIG_MODE_NOVECTOR;

@@ -375,6 +375,30 @@ def test_nmf_max_iter_cap_and_reinit(joost):
     assert np.array_equal(again["W"], got["W"])
 
 
+def test_large_block_eigensolver_path():
+    """Blocks above cuSOLVER's 32,768-row limit go through cusolverMgSyevd; RSOPTSC_MG_MIN_N lowers the
+    switch-over so that a small problem exercises that path (fresh process: the threshold is read once)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from conftest import small_problem\n"
+        "from oracle import rsoptsc_oracle as O\n"
+        "from rsoptsc_b200 import api\n"
+        "p = small_problem(150, 260, seed=3)\n"
+        "ref = O.computeM(O.mask_from_idx(p['idx'], 260), p['X'], 0.5, literal=False)\n"
+        "got = api.computeM(None, p['X'], 0.5, idx=p['idx'])\n"
+        "rel = np.linalg.norm(got['Z'] - ref['Z']) / np.linalg.norm(ref['Z'])\n"
+        "assert got['iters'] == ref['iters'] and rel < 1e-6, (got['iters'], ref['iters'], rel)\n"
+        "print('mg path ok', rel)\n" % (root, os.path.join(root, "tests")))
+    env = dict(os.environ, RSOPTSC_MG_MIN_N="64")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "mg path ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_repeated_calls_are_deterministic():
     """Caching allocator / persistent workspaces: same inputs -> bit-identical outputs, run to run."""
     p = small_problem(120, 300, seed=8)
