@@ -7,6 +7,7 @@
 //                 block goes through cusolverMgSyevd on this process's device (probed in
 //                 scratch/mg_probe.cu: 33,000 rows in 36.8 s on one B200)
 #include <cusolverMg.h>
+#include <dlfcn.h>
 
 #include "internal.h"
 
@@ -23,9 +24,52 @@ static int64_t mg_threshold() {
   return t;
 }
 
+// libcusolverMg is loaded on demand: it needs the toolkit's own libcublas (12.9), and linking it
+// eagerly breaks loading in processes where an older libcublas.so.12 is already resident (e.g. after
+// `import torch`, whose wheels bundle 12.8).  Only blocks above 32,768 rows ever get here.
+namespace mg {
+decltype(&::cusolverMgCreate) Create;
+decltype(&::cusolverMgDestroy) Destroy;
+decltype(&::cusolverMgDeviceSelect) DeviceSelect;
+decltype(&::cusolverMgCreateDeviceGrid) CreateDeviceGrid;
+decltype(&::cusolverMgDestroyGrid) DestroyGrid;
+decltype(&::cusolverMgCreateMatrixDesc) CreateMatrixDesc;
+decltype(&::cusolverMgDestroyMatrixDesc) DestroyMatrixDesc;
+decltype(&::cusolverMgSyevd_bufferSize) Syevd_bufferSize;
+decltype(&::cusolverMgSyevd) Syevd;
+static void load() {
+  static bool done = false;
+  if (done) return;
+  void* h = dlopen("libcusolverMg.so.11", RTLD_NOW | RTLD_LOCAL);
+  if (!h) h = dlopen("/usr/local/cuda/lib64/libcusolverMg.so.11", RTLD_NOW | RTLD_LOCAL);
+  if (!h) {
+    const char* why = dlerror();
+    fail(4, __FILE__, __LINE__, std::string("a connected block above 32,768 cells needs libcusolverMg, which could not be "
+                                            "loaded: ") + (why ? why : "?"));
+  }
+#define RS_MG_SYM(name)                                                                    \
+  name = reinterpret_cast<decltype(name)>(dlsym(h, "cusolverMg" #name));                   \
+  if (!name) fail(4, __FILE__, __LINE__, "libcusolverMg: missing symbol cusolverMg" #name)
+  RS_MG_SYM(Create); RS_MG_SYM(Destroy); RS_MG_SYM(DeviceSelect); RS_MG_SYM(CreateDeviceGrid); RS_MG_SYM(DestroyGrid);
+  RS_MG_SYM(CreateMatrixDesc); RS_MG_SYM(DestroyMatrixDesc); RS_MG_SYM(Syevd_bufferSize); RS_MG_SYM(Syevd);
+#undef RS_MG_SYM
+  done = true;
+}
+}  // namespace mg
+#define cusolverMgCreate mg::Create
+#define cusolverMgDestroy mg::Destroy
+#define cusolverMgDeviceSelect mg::DeviceSelect
+#define cusolverMgCreateDeviceGrid mg::CreateDeviceGrid
+#define cusolverMgDestroyGrid mg::DestroyGrid
+#define cusolverMgCreateMatrixDesc mg::CreateMatrixDesc
+#define cusolverMgDestroyMatrixDesc mg::DestroyMatrixDesc
+#define cusolverMgSyevd_bufferSize mg::Syevd_bufferSize
+#define cusolverMgSyevd mg::Syevd
+
 static void sym_eig_mg(double* d_A, int64_t n, double* d_lam, bool vectors) {
   Context& c = ctx();
   RS_REQUIRE(n <= 2147483647LL / 2, "sym_eig: block too large");
+  mg::load();
   static cusolverMgHandle_t handle = nullptr;
   static int handle_dev = -1;
   if (!handle || handle_dev != c.device) {
