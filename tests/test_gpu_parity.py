@@ -95,6 +95,30 @@ def test_computeM_disconnected_support_matches_oracle():
     assert abs(got["E"] - ref["E"]) < 1e-8 * ref["E"]
 
 
+def test_computeM_default_tensor_core_path_vs_oracle():
+    """One connected block of 1,800 cells: large enough that the DEFAULT backend sends the Gram and the
+    reconstruction GEMMs of every SVT through the tcgen05 split-integer kernel (threshold 1,536).  The
+    oracle takes about a minute here."""
+    from rsoptsc_b200 import _lib
+    from rsoptsc_b200.synthetic import synthetic_lognorm
+    n, m, K = 1800, 250, 10
+    data, _ = synthetic_lognorm(m, n, seed=9)
+    X = O.normalize_columns(data)
+    emb = np.random.default_rng(9).random((n, 3))            # uniform cloud -> a single kNN component
+    idx = O.knn_indices(emb, K)
+    assert api.graph_components(1.0 - O.mask_from_idx(idx, n))["no"] == 1
+    assert _lib.load().rsoptsc_get_gemm_backend() == 1
+    api.timers(True)
+    got = api.computeM(None, X, 0.5, idx=idx)
+    used = api.phase_report().get("ozaki_gemm", {"calls": 0})["calls"]
+    api.timers(False)
+    assert used > 0                                           # the tensor-core path really ran
+    ref = O.computeM(O.mask_from_idx(idx, n), X, 0.5, literal=False)
+    assert got["iters"] == ref["iters"]
+    assert relF(got["Z"], ref["Z"]) < 1e-6
+    assert abs(got["E"] - ref["E"]) < 1e-8 * ref["E"]
+
+
 def test_computeM_dense_mask_signature():
     p = small_problem(100, 120, seed=5)
     n = 120
@@ -238,6 +262,19 @@ def test_full_size_properties_config2():
     allowed[np.arange(n)[:, None], idx] = True
     allowed |= allowed.T
     assert not np.any((W > 0) & ~allowed)
+    # independent arithmetic for the dense contractions (cuBLAS FP64 instead of the tcgen05 split-integer
+    # kernel): same iteration count and the same W to ~1e-12 -- a full-size check of the GEMM emulation
+    from rsoptsc_b200 import _lib
+    lib = _lib.load()
+    prev = lib.rsoptsc_get_gemm_backend()
+    lib.rsoptsc_set_gemm_backend(0)
+    try:
+        r0 = api.SimilarityM(0.5, data)
+    finally:
+        lib.rsoptsc_set_gemm_backend(prev)
+    assert r0["iters"] == r["iters"] and r0["K"] == K
+    assert relF(r0["W"], W) < 1e-9
+    assert abs(r0["E"] - r["E"]) < 1e-9 * r["E"]
     c = api.ClusterCells(W, n_clusters=k)
     assert np.allclose(c["H"].sum(axis=0), 1.0, atol=1e-10)
     assert c["labels"].min() >= 1 and c["labels"].max() <= k
