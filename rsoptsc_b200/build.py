@@ -54,7 +54,8 @@ def build(force=False, verbose=False):
             if r.returncode != 0:
                 raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if jobs or force or _stale(LIB, objs):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + LIBS
+        # RUNPATH to the toolkit so libcublas/libcusolver resolve even without LD_LIBRARY_PATH
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + LIBS + ["-Xlinker", "-rpath=/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
