@@ -233,6 +233,36 @@ double update_Y3(const Support& s, const double* d_Zs, const double* d_J, double
   return total > 0 ? total : 0.0;
 }
 
+// ---- upper triangle <- lower triangle (column-major d x d) -----------------------------------
+__global__ void k_mirror_lower(double* __restrict__ B, int64_t d, int64_t j0) {
+  const int64_t j = j0 + blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < j; i += (int64_t)gridDim.x * 256) B[i + j * d] = B[j + i * d];
+}
+void mirror_lower(double* d_B, int64_t d) {
+  for (int64_t j0 = 1; j0 < d; j0 += 65535) {  // column 0 has nothing above the diagonal
+    const int64_t nc = std::min<int64_t>(65535, d - j0);
+    dim3 grid((unsigned)std::min<int64_t>(cdiv(d, 256), 16), (unsigned)nc);
+    RS_LAUNCH(k_mirror_lower, grid, 256, 0, d_B, d, j0);
+  }
+}
+
+// ---- dst[:, c] = src[:, c] * scale[c] ----------------------------------------------------------
+__global__ void k_copy_scale_columns(const double* __restrict__ src, int64_t rows, const double* __restrict__ scale,
+                                     double* __restrict__ dst) {
+  const double sc = scale[blockIdx.y];
+  const double* s = src + (int64_t)blockIdx.y * rows;
+  double* d = dst + (int64_t)blockIdx.y * rows;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = s[i] * sc;
+}
+void copy_scale_columns(const double* d_src, int64_t rows, int64_t cols, const double* d_scale, double* d_dst) {
+  for (int64_t c0 = 0; c0 < cols; c0 += 65535) {
+    const int64_t nc = std::min<int64_t>(65535, cols - c0);
+    dim3 grid((unsigned)std::min<int64_t>(cdiv(rows, 256), 8), (unsigned)nc);
+    RS_LAUNCH(k_copy_scale_columns, grid, 256, 0, d_src + c0 * rows, rows, d_scale + c0, d_dst + c0 * rows);
+  }
+}
+
 // ---- T[:, c] *= scale[c] --------------------------------------------------------------
 __global__ void k_scale_columns(double* __restrict__ T, int64_t rows, const double* __restrict__ scale) {
   const double sc = scale[blockIdx.y];

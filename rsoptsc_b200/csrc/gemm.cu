@@ -9,6 +9,7 @@
 namespace rs {
 
 void ozaki_gram_AtA(const double* A, int64_t rows, int64_t cols, double* G);
+void ozaki_gram_AAt(const double* A, int64_t rows, int64_t cols, double* G);
 void ozaki_gemm_nn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
 void ozaki_gemm_nt(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
 void ozaki_gemm_tn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
@@ -39,6 +40,7 @@ void gram_AtA(const double* A, int64_t rows, int64_t cols, double* G) {
                         &zero, G, (int)cols));
 }
 void gram_AAt(const double* A, int64_t rows, int64_t cols, double* G) {
+  if (use_ozaki(rows, rows, cols)) return ozaki_gram_AAt(A, rows, cols, G);
   const double one = 1.0, zero = 0.0;
   RS_CUBLAS(cublasDsyrk(ctx().cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)rows, (int)cols, &one, A, (int)rows,
                         &zero, G, (int)rows));

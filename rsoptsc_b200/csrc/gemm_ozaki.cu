@@ -486,6 +486,11 @@ void ozaki_gram_AtA(const double* A, int64_t rows, int64_t cols, double* G) {
   oz::slice_operand(A, rows, cols, rows, /*contig=*/true, ozaki_slices(), op);
   oz::run(op, op, G, cols, cols, cols, /*lower_only=*/true, false);
 }
+void ozaki_gram_AAt(const double* A, int64_t rows, int64_t cols, double* G) {  // G (rows x rows, lower) = A A^T
+  oz::Operand op;
+  oz::slice_operand(A, rows, rows, cols, /*contig=*/false, ozaki_slices(), op);
+  oz::run(op, op, G, rows, rows, rows, /*lower_only=*/true, false);
+}
 void ozaki_gemm_nn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K) {
   oz::Operand a, b;
   oz::slice_operand(A, M, M, K, /*contig=*/false, ozaki_slices(), a);

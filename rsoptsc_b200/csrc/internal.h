@@ -55,6 +55,8 @@ void gather_support_term(const Support& s, const double* d_Zs, const double* d_J
 // Y3 += mu*(Z - J) ; returns ||Z - J||_F^2   (J may be null == 0)
 double update_Y3(const Support& s, const double* d_Zs, const double* d_J, double mu, double* d_Y3);
 void scale_columns(double* d_T, int64_t rows, int64_t cols, const double* d_scale);
+void copy_scale_columns(const double* d_src, int64_t rows, int64_t cols, const double* d_scale, double* d_dst);
+void mirror_lower(double* d_B, int64_t d);  // upper triangle <- lower triangle
 void threshold_symmetrise_dense(const double* d_Z, int64_t n, double* d_W);
 void threshold_symmetrise_sparse(const Support& s, const double* d_Zs, double* d_W /* n x n, zeroed here */);
 void scatter_support_dense(const Support& s, const double* d_Zs, double* d_Z /* n x n, zeroed here */);
@@ -91,7 +93,7 @@ void sym_eig(double* d_A, int64_t n, double* d_lam, bool vectors);
 
 struct SvtWorkspace {
   int64_t n = 0;
-  DevBuf<double> G, T, lam;
+  DevBuf<double> G, T, B, lam;
   void ensure(int64_t n);
 };
 // J = SVT_tau(A) written over A.  Returns rank(J).

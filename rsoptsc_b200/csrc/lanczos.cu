@@ -326,12 +326,6 @@ void Lanczos::ritz_vectors(const std::vector<double>& S, const std::vector<int>&
 }
 
 // ---- spectral norm ------------------------------------------------------------------------
-// upper triangle <- lower triangle (column-major d x d)
-__global__ void k_mirror_lower(double* __restrict__ B, int64_t d) {
-  const int64_t j = blockIdx.y;
-  for (int64_t i = (int64_t)blockIdx.x * LT + threadIdx.x; i < j; i += (int64_t)gridDim.x * LT) B[i + j * d] = B[j + i * d];
-}
-
 double spectral_norm(const double* d_M, int64_t rows, int64_t cols, double rel_tol) {
   Phase ph("lanczos");
   if (rows == 0 || cols == 0) return 0.0;
@@ -345,10 +339,7 @@ double spectral_norm(const double* d_M, int64_t rows, int64_t cols, double rel_t
     // then one L2-resident symmetric matvec instead of two HBM streams over the m x n matrix
     B.alloc((size_t)d * d);
     if (small_rows) gram_AAt(d_M, rows, cols, B.p); else gram_AtA(d_M, rows, cols, B.p);
-    if (d > 1) {
-      dim3 grid((unsigned)std::min<int64_t>(cdiv(d, LT), 16), (unsigned)d);
-      RS_LAUNCH(k_mirror_lower, grid, LT, 0, B.p, d);
-    }
+    mirror_lower(B.p, d);
     mv.init(B.p, d, d);
     lz.init(d, 320, [&](const double* v, double* w) { mv.mul_t(v, w); });  // B symmetric: B^T v = B v
   } else {
