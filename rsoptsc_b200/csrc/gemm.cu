@@ -40,7 +40,8 @@ void gram_AtA(const double* A, int64_t rows, int64_t cols, double* G) {
                         &zero, G, (int)cols));
 }
 void gram_AAt(const double* A, int64_t rows, int64_t cols, double* G) {
-  if (use_ozaki(rows, rows, cols)) return ozaki_gram_AAt(A, rows, cols, G);
+  // few output tiles (rows < 4096 -> less than ~3 waves of 128 x 128 tiles) do not amortise the slicing
+  if (rows >= 4096 && use_ozaki(rows, rows, cols)) return ozaki_gram_AAt(A, rows, cols, G);
   const double one = 1.0, zero = 0.0;
   RS_CUBLAS(cublasDsyrk(ctx().cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)rows, (int)cols, &one, A, (int)rows,
                         &zero, G, (int)rows));
