@@ -1,0 +1,527 @@
+// Householder tridiagonalisation of a dense symmetric matrix (lower triangle), the memory-bound
+// first half of the symmetric eigensolver behind the SVT (a4: R/SimilarityM.R:142-155 needs the
+// spectrum of A^T A), the PCA (a2) and the Laplacian spectrum (a14).
+//
+// Same factorisation and storage as LAPACK dsytrd(uplo='L') -- Q = H(1) ... H(n-1),
+// H(i) = I - tau_i v_i v_i^T, v_i(i+1) = 1, v_i(i+2:n) stored below the subdiagonal of column i --
+// so a LAPACK-convention back-transformation (ormtr) applies.  Design for B200:
+//
+//  * one persistent cooperative kernel per panel of NB columns, one 512-thread CTA per SM, with a
+//    hand-rolled grid barrier + all-reduce (3 per column) instead of ~15 tiny launches per column
+//    (a flag-with-data variant where every CTA polls every slot was measured slower: the polls
+//    saturate L2);
+//  * the trailing-matrix product y = A22 v reads ONLY the lower triangle (half the bytes of a
+//    gemv).  The triangle is cut into strips of 64 rows x 16 columns, enumerated along block rows;
+//    every warp of the grid owns one contiguous run of strips (static, equal to within one strip).
+//    Lanes own rows (coalesced 256-byte column segments), row sums stay in registers along the
+//    run, column sums go through a transposing shuffle butterfly;
+//  * every partial sum has its own slot in a scratch array that is reduced in a fixed order, so
+//    results are bit-reproducible;
+//  * the rank-2NB trailing update between panels is one cublasDsyr2k.
+//
+// HBM traffic: sum_j 4 (n-j)^2 = (4/3) n^3 bytes for the products (the floor of any one-stage
+// tridiagonalisation) + 16 n^3 / (3 NB) for the trailing updates.
+#pragma once
+#include <cublas_v2.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+
+namespace rs {
+namespace sytrd {
+
+constexpr int NB = 64;          // panel width
+constexpr int THREADS = 512;    // 16 warps per CTA, one CTA per SM
+constexpr int MAX_GRID = THREADS;  // every CTA polls one slot per thread
+constexpr int TILE = 64;        // block edge of the triangle (rows per strip)
+constexpr int SW = 16;          // strip width (columns)
+constexpr int SPT = TILE / SW;  // strips per 64 x 64 block
+constexpr int TPR = 8;          // threads per row in the row-wise phases
+constexpr int RPT = NB / TPR;   // panel columns per thread in the row-wise phases
+constexpr int DOT_CHUNK = 512;  // rows per panel dot-product unit (about the cost of one strip)
+
+struct Params {
+  double* A;
+  long long lda;
+  int n;
+  int j0, pw;        // panel: columns j0 .. j0+pw-1
+  double* W;         // n x NB, leading dimension n, rows indexed globally
+  double* d;         // n
+  double* e;         // n-1
+  double* tau;       // n-1
+  double* rowpart;   // (warps + mB + 1) x 64 : slot (g + b) = row sums of warp g over block row b
+  double* colpart;   // mB x n : colpart[I*n + c] = sum over rows of block I of A[r,c] v[r]
+  double* abuf;      // 2 x n  : updated column (double-buffered by column parity)
+  double* wt;        // n      : w before the final alpha correction
+  double* pvec;      // chunks x 2 NB : partial W^T v and V^T v per chunk of DOT_CHUNK rows
+  unsigned long long* slots;  // 4 MAX_GRID words of per-CTA partials (double-buffered) + arrival counter + generation flag
+  long long* prof;   // optional cycle counters (null = off): [0..15] phases of CTA 0, [16 + cta] phase 3
+  int mB;            // ceil(n / 64)
+};
+
+__device__ __forceinline__ double warp_sum_fixed(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Grid-wide barrier + sum of two doubles per CTA.  Valid inputs in thread 0 of each CTA; every thread
+// of every CTA returns the same two sums (fixed summation order).  All global writes made by any CTA
+// before the call are visible to every CTA after it (release on the arrival counter, acquire on the
+// generation flag; bar.sync extends both to the whole CTA).  All CTAs are co-resident (cooperative
+// launch); the arrival counter is monotonic within a launch.
+__device__ __forceinline__ void grid_allreduce2(unsigned long long* slots, unsigned nblocks, unsigned& gen, double& v0,
+                                                double& v1, double* s_a, double* s_b, double* s_out) {
+  const unsigned tid = threadIdx.x;
+  ++gen;
+  double* part = reinterpret_cast<double*>(slots) + (size_t)(gen & 1u) * MAX_GRID * 2;  // double-buffered partials
+  unsigned* bar = reinterpret_cast<unsigned*>(slots + 4 * MAX_GRID);                    // [0] arrivals, [1] generation
+  __syncthreads();
+  if (tid == 0) {
+    part[2 * blockIdx.x] = v0;
+    part[2 * blockIdx.x + 1] = v1;
+    unsigned ticket;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(bar) : "memory");
+    if (ticket == gen * nblocks - 1u) {
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen) : "memory");
+    } else {
+      unsigned spins = 0, seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar + 1) : "memory");
+        if (++spins > (1u << 25)) __trap();  // never hang the device
+      } while (seen < gen);
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    double a = 0, b = 0;
+    for (unsigned k = tid; k < nblocks; k += 32) {
+      a += part[2 * k];
+      b += part[2 * k + 1];
+    }
+    a = warp_sum_fixed(a);
+    b = warp_sum_fixed(b);
+    if (tid == 0) { s_out[0] = a; s_out[1] = b; }
+  }
+  __syncthreads();
+  v0 = s_out[0];
+  v1 = s_out[1];
+  (void)s_a;
+  (void)s_b;
+}
+
+// CTA-wide sum of two values; result valid in thread 0.
+__device__ __forceinline__ void cta_reduce2(double& a, double& b, double* s_tmp /* 2 x 16 */) {
+  a = warp_sum_fixed(a);
+  b = warp_sum_fixed(b);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_tmp[w] = a; s_tmp[16 + w] = b; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    a = threadIdx.x < (THREADS >> 5) ? s_tmp[threadIdx.x] : 0.0;
+    b = threadIdx.x < (THREADS >> 5) ? s_tmp[16 + threadIdx.x] : 0.0;
+    a = warp_sum_fixed(a);
+    b = warp_sum_fixed(b);
+  }
+}
+
+// Transposing butterfly: every lane holds 16 partial column sums; on return every lane holds the
+// complete sum of ONE column, index = bit4*8 + bit3*4 + bit2*2 + bit1 of the lane id.
+__device__ __forceinline__ double butterfly16(double (&p)[16], int lane) {
+  double q8[8], q4[4], q2[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const double send = b4 ? p[k] : p[k + 8];
+    const double keep = b4 ? p[k + 8] : p[k];
+    q8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double send = b3 ? q8[k] : q8[k + 4];
+    const double keep = b3 ? q8[k + 4] : q8[k];
+    q4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double send = b2 ? q4[k] : q4[k + 2];
+    const double keep = b2 ? q4[k + 2] : q4[k];
+    q2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const double send = b1 ? q2[0] : q2[1];
+  const double keep = b1 ? q2[1] : q2[0];
+  double r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
+// Work units of phase 3, in this order: the strips of block row b = 0, 1, ... (block row b has
+// SPT (b + 1) strips, the first at unit SPT b (b + 1) / 2), then the panel dot-product chunks.
+// Unit u belongs to warp owner(u) = floor(u * nw / total) with nw = min(warps, total): contiguous
+// runs, equal to within one unit, and every warp below nw owns at least one unit.
+struct UnitMap {
+  long long strips, total, nw;
+  __device__ __forceinline__ long long first_of_row(int b) const { return (long long)SPT * b * (b + 1) / 2; }
+  __device__ __forceinline__ long long start(long long g) const { return (g * total + nw - 1) / nw; }  // ceil
+  __device__ __forceinline__ long long owner(long long u) const { return u * nw / total; }
+};
+
+__global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
+  __shared__ double s_tmp[32];
+  __shared__ double s_ra[MAX_GRID], s_rb[MAX_GRID], s_out[2];  // grid all-reduce staging
+  __shared__ double s_p1[NB], s_p2[NB];                        // W^T v, V^T v (phase 4)
+  __shared__ double s_vj[THREADS / 32][SW];                    // per-warp copy of v over the strip's columns
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned nblocks = gridDim.x;
+  const int n = P.n;
+  const long long lda = P.lda;
+  double* A = P.A;
+  double* W = P.W;
+  const long long ldw = n;
+  unsigned gen = 0;
+
+  const int gthreads = nblocks * THREADS;
+  const int gtid = blockIdx.x * THREADS + tid;
+  const int slot = gtid / TPR, sub = gtid % TPR, nslots = gthreads / TPR;
+  const int gwarp = blockIdx.x * (THREADS / 32) + warp;
+  const long long nwarps = (long long)nblocks * (THREADS / 32);
+
+  double tau_prev = 0, scale_prev = 0, alpha2_prev = 0;  // of column j-1 (uniform across the grid)
+
+  const bool prof = P.prof != nullptr && blockIdx.x == 0 && tid == 0;
+  long long tc = prof ? clock64() : 0;
+#define RS_PROF(k) if (prof) { const long long t_ = clock64(); P.prof[k] += t_ - tc; tc = t_; }
+  for (int jj = 0; jj < P.pw; ++jj) {
+    const int j = P.j0 + jj;
+    double* ab = P.abuf + (size_t)(j & 1) * n;               // this column, updated
+    const double* abp = P.abuf + (size_t)((j - 1) & 1) * n;  // previous column (gives v_{j-1})
+
+    // ---------------- phase 1: finish W(:, jj-1), update column j, norm of its tail ------------
+    // a(i) = A(i,j) - sum_t V(i,t) W(j,t) + W(i,t) V(j,t); every load of a row is issued in one batch.
+    double ss = 0, alpha_part = 0;
+    for (int base = j; base < n; base += nslots) {  // trip count uniform across the grid (shuffles below)
+      const int i = base + slot;
+      const bool live = i < n;
+      const double a_ij = (live && sub == 0) ? A[i + (long long)j * lda] : 0.0;
+      double wlast_i = 0, wlast_j = 0;
+      if (live && jj > 0) {
+        const double vprev = (i == j) ? 1.0 : abp[i] * scale_prev;
+        wlast_i = P.wt[i] + alpha2_prev * vprev;  // final value of W(i, jj-1)
+        wlast_j = P.wt[j] + alpha2_prev;          // final value of W(j, jj-1)   (v_{j-1}(j) = 1)
+      }
+      double vi[RPT], wi[RPT], vj[RPT], wj[RPT];
+#pragma unroll
+      for (int u = 0; u < RPT; ++u) {
+        const int t = sub + u * TPR;
+        const bool on = live && t < jj;
+        const bool old = on && t != jj - 1;
+        vi[u] = on ? A[i + (long long)(P.j0 + t) * lda] : 0.0;
+        vj[u] = on ? A[j + (long long)(P.j0 + t) * lda] : 0.0;
+        wi[u] = old ? W[i + (long long)t * ldw] : 0.0;
+        wj[u] = old ? W[j + (long long)t * ldw] : 0.0;
+      }
+      double acc = 0;
+#pragma unroll
+      for (int u = 0; u < RPT; ++u) {
+        const int t = sub + u * TPR;
+        if (live && t < jj) {
+          double wit = wi[u], wjt = wj[u];
+          if (t == jj - 1) {
+            wit = wlast_i;
+            wjt = wlast_j;
+            W[i + (long long)t * ldw] = wit;
+          }
+          acc += vi[u] * wjt + wit * vj[u];
+        }
+      }
+#pragma unroll
+      for (int o = 1; o < TPR; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (sub == 0 && live) {
+        const double a = a_ij - acc;
+        ab[i] = a;
+        if (i == j) P.d[j] = a;
+        else if (i == j + 1) alpha_part = a;
+        else ss += a * a;
+      }
+    }
+    RS_PROF(0)
+    cta_reduce2(ss, alpha_part, s_tmp);
+    grid_allreduce2(P.slots, nblocks, gen, ss, alpha_part, s_ra, s_rb, s_out);  // #1: ||x||^2 and alpha
+    RS_PROF(1)
+
+    // ---------------- phase 2: reflector (every thread, identical arithmetic) -------------------
+    double tau = 0, scale = 0;
+    {
+      const double alpha = alpha_part, xn2 = ss;
+      double beta = alpha;
+      if (xn2 > 0) {
+        beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+        tau = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+      }
+      if (gtid == 0) { P.e[j] = beta; P.tau[j] = tau; }
+    }
+    // store v in the matrix (owners only; readers use ab[] * scale)
+    for (int i = j + 1 + gtid; i < n; i += gthreads) A[i + (long long)j * lda] = (i == j + 1) ? 1.0 : ab[i] * scale;
+
+    // ---------------- phase 3: y = A22 v over the lower triangle; panel dot products ------------
+    const long long t3 = (P.prof != nullptr && tid == 0) ? clock64() : 0;
+    const int Bmin = (j + 1) / TILE;
+    const int mt = P.mB - Bmin;
+    const int nch = (n - j - 1 + DOT_CHUNK - 1) / DOT_CHUNK;  // row chunks of the panel dot products
+    UnitMap um;
+    um.strips = um.first_of_row(mt);
+    um.total = um.strips + 2LL * jj * nch;
+    um.nw = nwarps < um.total ? nwarps : um.total;
+    if (gwarp < um.nw) {
+      long long u = um.start(gwarp);
+      const long long uend = um.start(gwarp + 1);
+      if (u < um.strips) {
+        // locate the first strip: block row b (relative to Bmin), position k inside the row
+        int b = (int)floor((sqrt(1.0 + 8.0 * (double)u / SPT) - 1.0) * 0.5);
+        if (b < 0) b = 0;
+        while (b > 0 && um.first_of_row(b) > u) --b;
+        while (um.first_of_row(b + 1) <= u) ++b;
+        int k = (int)(u - um.first_of_row(b));
+        double rs0 = 0, rs1 = 0, vi0 = 0, vi1 = 0;
+        bool newrow = true;
+        const long long send = uend < um.strips ? uend : um.strips;
+        for (; u < send; ++u) {
+          const int I = Bmin + b, J = Bmin + k / SPT, pass = k % SPT;
+          const int r0i = I * TILE + lane, r1i = r0i + 32;
+          const bool ok0 = r0i < n, ok1 = r1i < n;
+          const int cbase = J * TILE + pass * SW;  // first column of the strip
+          // matrix loads first (the long latency), then the pieces of v
+          double a0[SW], a1[SW], p[SW];
+          const double* Ab = A + (long long)cbase * lda;
+#pragma unroll
+          for (int c = 0; c < SW; ++c) {
+            const bool okc = cbase + c < n;
+            const double* col = Ab + (long long)c * lda;
+            a0[c] = (ok0 && okc) ? __ldcs(col + r0i) : 0.0;  // streaming: do not evict the panel from L2
+            a1[c] = (ok1 && okc) ? __ldcs(col + r1i) : 0.0;
+          }
+          if (newrow) {
+            vi0 = (ok0 && r0i > j) ? (r0i == j + 1 ? 1.0 : ab[r0i] * scale) : 0.0;
+            vi1 = (ok1 && r1i > j) ? (r1i == j + 1 ? 1.0 : ab[r1i] * scale) : 0.0;
+            newrow = false;
+          }
+          {
+            const int c = cbase + (lane & (SW - 1));
+            const double v = (c < n && c > j) ? (c == j + 1 ? 1.0 : ab[c] * scale) : 0.0;
+            __syncwarp();
+            if (lane < SW) s_vj[warp][lane] = v;
+            __syncwarp();
+          }
+          if (I != J) {
+#pragma unroll
+            for (int c = 0; c < SW; ++c) {
+              const double vj = s_vj[warp][c];
+              rs0 += a0[c] * vj;
+              rs1 += a1[c] * vj;
+              p[c] = a0[c] * vi0 + a1[c] * vi1;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < SW; ++c) {
+              const int cl = pass * SW + c;  // column inside the 64 x 64 diagonal block
+              const double vj = s_vj[warp][c];
+              // local rows: lane and lane+32; lower triangle incl. diagonal feeds the row sums,
+              // the strict lower triangle feeds the column sums (the upper triangle is never used)
+              const double x0 = (lane >= cl) ? a0[c] : 0.0;
+              const double x1 = (lane + 32 >= cl) ? a1[c] : 0.0;
+              rs0 += x0 * vj;
+              rs1 += x1 * vj;
+              const double y0 = (lane > cl) ? a0[c] : 0.0;
+              const double y1 = (lane + 32 > cl) ? a1[c] : 0.0;
+              p[c] = y0 * vi0 + y1 * vi1;
+            }
+          }
+          const double cs = butterfly16(p, lane);
+          if (!(lane & 1)) {
+            const int cg = cbase + ((lane >> 1) & 15);
+            if (cg < n) P.colpart[(size_t)I * n + cg] = cs;
+          }
+          // advance; flush the row sums at the end of a block row or of the run
+          ++k;
+          const bool endrow = (k == SPT * (b + 1));
+          if (endrow || u + 1 == send) {
+            double* rp = P.rowpart + (size_t)(gwarp + b) * TILE;
+            rp[lane] = rs0;
+            rp[lane + 32] = rs1;
+            rs0 = rs1 = 0;
+          }
+          if (endrow) { ++b; k = 0; newrow = true; }
+        }
+      }
+      // dot-product units: q < jj -> W(:,q)^T v ; q >= jj -> V(:,q-jj)^T v, over one chunk of rows
+      for (; u < uend; ++u) {
+        const int r = (int)(u - um.strips);
+        const int q = r / nch, ch = r - q * nch;
+        const double* colp = (q < jj) ? (W + (long long)q * ldw) : (A + (long long)(P.j0 + q - jj) * lda);
+        const int ibeg = j + 1 + ch * DOT_CHUNK;
+        const int iend = min(n, ibeg + DOT_CHUNK);
+        double acc = 0;
+#pragma unroll 8
+        for (int i = ibeg + lane; i < iend; i += 32) {
+          const double vi = (i == j + 1) ? 1.0 : ab[i] * scale;
+          acc += colp[i] * vi;
+        }
+        acc = warp_sum_fixed(acc);
+        if (lane == 0) P.pvec[(size_t)ch * (2 * NB) + q] = acc;
+      }
+    }
+    RS_PROF(2)
+    if (P.prof != nullptr && tid == 0) { P.prof[16 + blockIdx.x] += clock64() - t3; }
+    {
+      double z0 = 0, z1 = 0;
+      grid_allreduce2(P.slots, nblocks, gen, z0, z1, s_ra, s_rb, s_out);  // #2: plain barrier
+    }
+    RS_PROF(3)
+
+    // ---------------- phase 4: w = tau (y - V p1 - W p2), partial w.v -----------------------------
+    double dotp = 0;
+    bool first = true;
+    for (int base = j + 1; base < n; base += nslots) {
+      const int i = base + slot;
+      const bool live = i < n;
+      const int Ii = i / TILE, b = Ii - Bmin;
+      double vv[RPT], ww[RPT];
+#pragma unroll
+      for (int u = 0; u < RPT; ++u) {
+        const int t = sub + u * TPR;
+        const bool on = live && t < jj;
+        vv[u] = on ? A[i + (long long)(P.j0 + t) * lda] : 0.0;
+        ww[u] = on ? W[i + (long long)t * ldw] : 0.0;
+      }
+      double acc = 0;
+      if (live) {
+        // row parts: the warps whose runs intersect block row b, slot (g + b); column parts: block rows Ii..mB-1
+        const long long s0 = um.first_of_row(b);
+        const int g0 = (int)um.owner(s0), g1 = (int)um.owner(s0 + (long long)SPT * (b + 1) - 1);
+        const int nrow = g1 - g0 + 1, ncol = P.mB - Ii;
+        const double* rp = P.rowpart + (size_t)(g0 + b) * TILE + (i - Ii * TILE);
+        const double* cp = P.colpart + ((long long)(Ii - nrow) * n + i);  // k >= nrow -> block row Ii + (k - nrow)
+        const int ntot = nrow + ncol;
+#pragma unroll 8
+        for (int k = sub; k < ntot; k += TPR) acc += (k < nrow) ? rp[(size_t)k * TILE] : cp[(size_t)k * n];
+      }
+      if (first) {
+        // panel dot products: sum the row chunks (4 threads per product), overlapped with the loads above
+        first = false;
+        const int q = tid >> 2, c4 = tid & 3;
+        double pa = 0;
+        if (q < 2 * jj)
+          for (int ch = c4; ch < nch; ch += 4) pa += P.pvec[(size_t)ch * (2 * NB) + q];
+        pa += __shfl_xor_sync(0xffffffffu, pa, 1);
+        pa += __shfl_xor_sync(0xffffffffu, pa, 2);
+        if (c4 == 0 && q < 2 * jj) {
+          if (q < jj) s_p1[q] = pa;
+          else s_p2[q - jj] = pa;
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int u = 0; u < RPT; ++u) {
+        const int t = sub + u * TPR;
+        if (live && t < jj) acc -= vv[u] * s_p1[t] + ww[u] * s_p2[t];
+      }
+#pragma unroll
+      for (int o = 1; o < TPR; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (sub == 0 && live) {
+        const double wi = tau * acc;
+        P.wt[i] = wi;
+        const double vi = (i == j + 1) ? 1.0 : ab[i] * scale;
+        dotp += wi * vi;
+      }
+    }
+    RS_PROF(4)
+    {
+      double z = 0;
+      cta_reduce2(dotp, z, s_tmp);
+      grid_allreduce2(P.slots, nblocks, gen, dotp, z, s_ra, s_rb, s_out);  // #3: w.v
+    }
+    alpha2_prev = -0.5 * tau * dotp;
+    tau_prev = tau;
+    scale_prev = scale;
+    RS_PROF(5)
+  }
+#undef RS_PROF
+
+  // final correction of the last panel column
+  {
+    const int jj = P.pw - 1, j = P.j0 + jj;
+    const double* ab = P.abuf + (size_t)(j & 1) * n;
+    for (int i = j + 1 + gtid; i < n; i += gthreads) {
+      const double vi = (i == j + 1) ? 1.0 : ab[i] * scale_prev;
+      W[i + (long long)jj * ldw] = P.wt[i] + alpha2_prev * vi;
+    }
+  }
+  (void)tau_prev;
+}
+
+__global__ void k_restore_subdiag(double* A, long long lda, int n, const double* e, double* d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n - 1) A[(i + 1) + (long long)i * lda] = e[i];
+  if (i == n - 1) d[n - 1] = A[(long long)(n - 1) * lda + (n - 1)];
+}
+
+inline size_t rowpart_doubles(int64_t n) {
+  const int64_t mB = (n + TILE - 1) / TILE;
+  return (size_t)(MAX_GRID * (THREADS / 32) + mB + 1) * TILE;
+}
+inline size_t workspace_doubles(int64_t n) {
+  const int64_t mB = (n + TILE - 1) / TILE;
+  return (size_t)n * NB + rowpart_doubles(n) + (size_t)mB * n + 2 * n + n + 2 * NB * (n / DOT_CHUNK + 1) +
+         4 * MAX_GRID + 8 + 64;
+}
+
+// A: n x n column-major, lower triangle referenced.  work: workspace_doubles(n) doubles (256-byte aligned).
+// Returns cudaSuccess or the failing status; launches counted in *launches.
+inline cudaError_t run(cublasHandle_t blas, cudaStream_t stream, double* A, int64_t n, int64_t lda, double* d, double* e,
+                       double* tau, double* work, int64_t* launches, long long* prof = nullptr) {
+  if (n < 1) return cudaSuccess;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = sms < MAX_GRID ? sms : MAX_GRID;
+  const int64_t mB = (n + TILE - 1) / TILE;
+  Params P;
+  P.A = A; P.lda = lda; P.n = (int)n; P.d = d; P.e = e; P.tau = tau; P.mB = (int)mB;
+  double* w = work;
+  P.W = w;        w += (size_t)n * NB;
+  P.rowpart = w;  w += rowpart_doubles(n);
+  P.colpart = w;  w += (size_t)mB * n;
+  P.abuf = w;     w += 2 * n;
+  P.wt = w;       w += n;
+  P.pvec = w;     w += 2 * NB * (n / DOT_CHUNK + 1);
+  P.slots = reinterpret_cast<unsigned long long*>(w);
+  P.prof = prof;
+  cublasSetStream(blas, stream);
+  for (int64_t j0 = 0; j0 < n - 1; j0 += NB) {
+    const int pw = (int)((n - 1 - j0) < NB ? (n - 1 - j0) : NB);
+    P.j0 = (int)j0; P.pw = pw;
+    // generation numbers restart at 1 in every launch: clear the flags
+    cudaError_t st = cudaMemsetAsync(P.slots, 0, sizeof(unsigned long long) * (4 * MAX_GRID + 8), stream);
+    if (st != cudaSuccess) return st;
+    void* args[] = {&P};
+    st = cudaLaunchCooperativeKernel((void*)k_latrd_panel, dim3(grid), dim3(THREADS), args, 0, stream);
+    if (st != cudaSuccess) return st;
+    if (launches) ++*launches;
+    const int64_t r0 = j0 + pw, nr = n - r0;  // trailing block
+    if (nr > 0) {
+      const double mone = -1.0, one = 1.0;
+      cublasStatus_t bs = cublasDsyr2k(blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)nr, pw, &mone, A + r0 + j0 * lda,
+                                       (int)lda, P.W + r0, (int)n, &one, A + r0 + r0 * lda, (int)lda);
+      if (bs != CUBLAS_STATUS_SUCCESS) return cudaErrorUnknown;
+    }
+  }
+  k_restore_subdiag<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(A, lda, (int)n, e, d);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+}  // namespace sytrd
+}  // namespace rs
