@@ -194,6 +194,15 @@ int32_t rsoptsc_get_gemm_backend(void);
 int rsoptsc_debug_gemm(int32_t op, const double* A, const double* B, double* C, int64_t M,
                        int64_t N, int64_t K, int32_t backend, int32_t reps, double* ms_out);
 
+/* Symmetric eigen-decomposition of a host matrix (n x n column-major, lower triangle referenced) with
+ * one of the two solvers behind the SVT of rsoptsc_computeM (R/SimilarityM.R:142-155):
+ *   solver 0: cuSOLVER syevd;  solver 1: native (cooperative-kernel tridiagonalisation, tridiagonal
+ *   divide and conquer with tcgen05 GEMMs, library back-transformation).
+ * lam_out (n) ascending eigenvalues, V_out (n x n, may be NULL) eigenvectors.  reps >= 1 repetitions
+ * are timed with CUDA events; *ms_out (may be NULL) = mean ms per call. */
+int rsoptsc_debug_sym_eig(const double* A, int64_t n, int32_t solver, double* lam_out, double* V_out,
+                          int32_t reps, double* ms_out);
+
 /* ---- host-only helpers (no GPU needed; exercised by the CPU test-suite) ---------------- */
 /* Eigen-decomposition of a symmetric tridiagonal matrix (the small problem of every Lanczos
  * run): d (k) diagonal in / ascending eigenvalues out, e (k-1) off-diagonal, V (k x k

@@ -73,6 +73,7 @@ SIGNATURES = {
     "rsoptsc_get_gemm_backend": (C.c_int32, []),
     "rsoptsc_debug_gemm": (C.c_int, [C.c_int32, c_double_p, c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int64,
                                      C.c_int32, C.c_int32, c_double_p]),
+    "rsoptsc_debug_sym_eig": (C.c_int, [c_double_p, C.c_int64, C.c_int32, c_double_p, c_double_p, C.c_int32, c_double_p]),
     "rsoptsc_host_tridiag_eig": (C.c_int, [C.c_int32, c_double_p, c_double_p, c_double_p]),
     "rsoptsc_host_choose_K": (C.c_int32, [c_double_p, C.c_int64]),
 }

@@ -703,6 +703,35 @@ int rsoptsc_debug_gemm(int32_t op, const double* A, const double* B, double* C, 
   });
 }
 
+int rsoptsc_debug_sym_eig(const double* A, int64_t n, int32_t solver, double* lam_out, double* V_out, int32_t reps,
+                          double* ms_out) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(A && lam_out && n >= 1 && n <= 32768 && reps >= 1 && (solver == 0 || solver == 1), "debug_sym_eig: bad arguments");
+    const size_t nn = (size_t)n * n;
+    DevBuf<double> a0(nn), a(nn), lam(n);
+    a0.upload(A, nn, s);
+    cudaEvent_t e0, e1;
+    RS_CUDA(cudaEventCreate(&e0)); RS_CUDA(cudaEventCreate(&e1));
+    float total = 0;
+    for (int r = 0; r <= reps; ++r) {  // r == 0 is the warm-up
+      RS_CUDA(cudaMemcpyAsync(a.p, a0.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, s));
+      RS_CUDA(cudaEventRecord(e0, s));
+      sym_eig_select(a.p, n, lam.p, solver);
+      RS_CUDA(cudaEventRecord(e1, s));
+      RS_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      RS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (r > 0) total += ms;
+    }
+    if (ms_out) *ms_out = total / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    lam.download(lam_out, n, s);
+    if (V_out) a.download(V_out, nn, s);
+    RS_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
 int rsoptsc_host_tridiag_eig(int32_t k, double* d, const double* e, double* V) {
   return guarded([&] {
     RS_REQUIRE(k >= 1, "tridiag_eig: k must be positive");

@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 
 #include "internal.h"
+#include "sytrd_kernel.cuh"
 
 namespace rs {
 
@@ -112,11 +113,74 @@ static void sym_eig_mg(double* d_A, int64_t n, double* d_lam, bool vectors) {
   RS_CUDA(cudaStreamSynchronize(c.stream));
 }
 
+// ---- native solver: own tridiagonalisation (sytrd_kernel.cuh) + own tridiagonal divide and conquer
+// (stedc.cu, GEMMs on tcgen05) + the library's LAPACK-convention back-transformation (Dormtr) ----------
+void stedc_device(const double* d_d, const double* d_e, int64_t n, double* d_lam, double* d_Z, double* d_S1, double* d_S2);
+
+// RSOPTSC_EIG=cusolver forces the library path, RSOPTSC_EIG=native lowers the size threshold to 256
+// (parity tests); default: native from RSOPTSC_NATIVE_MIN_N rows (6000: below that cuSOLVER's lower per-column latency
+// wins, measured on B200: 4,000 rows 113 vs 85 ms, 7,954 rows 348 vs 440 ms) up to 32,768.
+static int64_t native_min_n() {
+  static int64_t t = -2;
+  if (t == -2) {
+    const char* mode = getenv("RSOPTSC_EIG");
+    const char* e = getenv("RSOPTSC_NATIVE_MIN_N");
+    if (mode && std::string(mode) == "cusolver") t = -1;
+    else if (mode && std::string(mode) == "native") t = 256;
+    else t = e ? std::max<int64_t>(atoll(e), 2) : 6000;
+  }
+  return t;
+}
+
+static void sym_eig_native(double* d_A, int64_t n, double* d_lam) {
+  Context& c = ctx();
+  DevBuf<double> d(n), e(n), tau(n), Z((size_t)n * n);
+  {
+    Phase ph("eig_sytrd");
+    DevBuf<double> work(sytrd::workspace_doubles(n));
+    int64_t launches = 0;
+    RS_CUDA(sytrd::run(c.cublas, c.stream, d_A, n, n, d.p, e.p, tau.p, work.p, &launches));
+    g_launches.fetch_add(launches, std::memory_order_relaxed);
+  }
+  {
+    Phase ph("eig_stedc");
+    DevBuf<double> S1((size_t)n * n), S2((size_t)n * n);
+    stedc_device(d.p, e.p, n, d_lam, Z.p, S1.p, S2.p);
+  }
+  {
+    Phase ph("eig_ormtr");
+    int lwork = 0;
+    RS_CUSOLVER(cusolverDnDormtr_bufferSize(c.cusolver, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)n, (int)n,
+                                            d_A, (int)n, tau.p, Z.p, (int)n, &lwork));
+    DevBuf<double> work((size_t)std::max(lwork, 1));
+    DevBuf<int> info(1);
+    RS_CUSOLVER(cusolverDnDormtr(c.cusolver, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)n, (int)n, d_A, (int)n,
+                                 tau.p, Z.p, (int)n, work.p, lwork, info.p));
+    int hinfo = 0;
+    RS_CUDA(cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    RS_CUDA(cudaMemcpyAsync(d_A, Z.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, c.stream));
+    RS_CUDA(cudaStreamSynchronize(c.stream));
+    RS_REQUIRE(hinfo == 0, "back-transformation failed (info=" + std::to_string(hinfo) + ")");
+  }
+}
+
+static void sym_eig_library(double* d_A, int64_t n, double* d_lam, bool vectors);
+
+void sym_eig_select(double* d_A, int64_t n, double* d_lam, int solver) {
+  if (solver == 1) return sym_eig_native(d_A, n, d_lam);
+  sym_eig_library(d_A, n, d_lam, true);
+}
+
 // A (n x n, lower triangle referenced) -> eigenvectors in A (when `vectors`), eigenvalues ascending
 // in d_lam.  Throws when the solver reports failure.
 void sym_eig(double* d_A, int64_t n, double* d_lam, bool vectors) {
-  Context& c = ctx();
   RS_REQUIRE(n >= 1, "sym_eig: empty matrix");
+  if (vectors && native_min_n() >= 0 && n >= native_min_n() && n <= 32768) return sym_eig_native(d_A, n, d_lam);
+  sym_eig_library(d_A, n, d_lam, vectors);
+}
+
+static void sym_eig_library(double* d_A, int64_t n, double* d_lam, bool vectors) {
+  Context& c = ctx();
   if (n > mg_threshold()) return sym_eig_mg(d_A, n, d_lam, vectors);
   static cusolverDnParams_t params = nullptr;
   if (!params) RS_CUSOLVER(cusolverDnCreateParams(&params));

@@ -12,6 +12,9 @@ void gram_AtA(const double* A, int64_t rows, int64_t cols, double* G);
 void gram_AAt(const double* A, int64_t rows, int64_t cols, double* G);
 // C (M x N) = A (M x K) * B (K x N)
 void gemm_nn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
+// same with explicit leading dimensions (sub-blocks of larger matrices)
+void gemm_nn_ld(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t N,
+                int64_t K);
 // C (M x N) = A (M x K) * B^T, B: N x K
 void gemm_nt(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
 // C (M x N) = A^T * B, A: K x M, B: K x N

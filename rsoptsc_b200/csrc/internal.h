@@ -90,6 +90,8 @@ void tridiag_eig(std::vector<double>& d, std::vector<double>& e, std::vector<dou
 // eig.cu: dense symmetric eigensolver (lower triangle of A; eigenvectors overwrite A when requested,
 // eigenvalues ascending in d_lam)
 void sym_eig(double* d_A, int64_t n, double* d_lam, bool vectors);
+// same with eigenvectors, solver forced: 0 library (cuSOLVER), 1 native (sytrd_kernel.cuh + stedc.cu)
+void sym_eig_select(double* d_A, int64_t n, double* d_lam, int solver);
 
 struct SvtWorkspace {
   int64_t n = 0;
