@@ -118,8 +118,8 @@ static void sym_eig_mg(double* d_A, int64_t n, double* d_lam, bool vectors) {
 void stedc_device(const double* d_d, const double* d_e, int64_t n, double* d_lam, double* d_Z, double* d_S1, double* d_S2);
 
 // RSOPTSC_EIG=cusolver forces the library path, RSOPTSC_EIG=native lowers the size threshold to 256
-// (parity tests); default: native from RSOPTSC_NATIVE_MIN_N rows (6000: below that cuSOLVER's lower per-column latency
-// wins, measured on B200: 4,000 rows 113 vs 85 ms, 7,954 rows 348 vs 440 ms) up to 32,768.
+// (parity tests); default: native from RSOPTSC_NATIVE_MIN_N rows (4000: below that cuSOLVER's lower per-column latency
+// wins, measured on B200: 4,000 rows 81 vs 84 ms, 5,000 rows 119 vs 145 ms, 7,954 rows 296 vs 437 ms) up to 32,768.
 static int64_t native_min_n() {
   static int64_t t = -2;
   if (t == -2) {
@@ -127,7 +127,7 @@ static int64_t native_min_n() {
     const char* e = getenv("RSOPTSC_NATIVE_MIN_N");
     if (mode && std::string(mode) == "cusolver") t = -1;
     else if (mode && std::string(mode) == "native") t = 256;
-    else t = e ? std::max<int64_t>(atoll(e), 2) : 6000;
+    else t = e ? std::max<int64_t>(atoll(e), 2) : 4000;
   }
   return t;
 }

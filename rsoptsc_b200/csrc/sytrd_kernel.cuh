@@ -7,9 +7,13 @@
 // so a LAPACK-convention back-transformation (ormtr) applies.  Design for B200:
 //
 //  * one persistent cooperative kernel per panel of NB columns, one 512-thread CTA per SM, with a
-//    hand-rolled grid barrier + all-reduce (3 per column) instead of ~15 tiny launches per column
-//    (a flag-with-data variant where every CTA polls every slot was measured slower: the polls
+//    hand-rolled grid barrier + all-reduce instead of ~15 tiny launches per column (a
+//    flag-with-data variant where every CTA polls every slot was measured slower: the polls
 //    saturate L2);
+//  * TWO grid synchronisations per column instead of the textbook three: v^T w, which fixes the
+//    symmetric correction w -= (tau/2)(w^T v) v, is obtained as tau (v^T A22 v - 2 (W^T v).(V^T v))
+//    from sums that the product phase accumulates anyway, so the correction, the final W column
+//    and the update of the NEXT column all happen in one phase that reads the panel once;
 //  * the trailing-matrix product y = A22 v reads ONLY the lower triangle (half the bytes of a
 //    gemv).  The triangle is cut into strips of 64 rows x 16 columns, enumerated along block rows;
 //    every warp of the grid owns one contiguous run of strips (static, equal to within one strip).
@@ -33,12 +37,15 @@ namespace sytrd {
 
 constexpr int NB = 64;          // panel width
 constexpr int THREADS = 512;    // 16 warps per CTA, one CTA per SM
-constexpr int MAX_GRID = THREADS;  // every CTA polls one slot per thread
+constexpr int MAX_GRID = 512;   // upper bound on the cooperative grid
 constexpr int TILE = 64;        // block edge of the triangle (rows per strip)
 constexpr int SW = 16;          // strip width (columns)
 constexpr int SPT = TILE / SW;  // strips per 64 x 64 block
-constexpr int TPR = 8;          // threads per row in the row-wise phases
-constexpr int RPT = NB / TPR;   // panel columns per thread in the row-wise phases
+constexpr int TPR = 8;          // threads per row in the row-wise phase
+constexpr int RPT = NB / TPR;   // panel columns per thread in the row-wise phase
+constexpr int KB = 24;          // partial sums of a row fetched per lane in one batch
+constexpr int ROW_WARPS = THREADS / 32 - 1;        // warps that sweep rows; the last warp handles row j+1
+constexpr int ROWS_PER_CTA = ROW_WARPS * (32 / TPR);
 constexpr int DOT_CHUNK = 512;  // rows per panel dot-product unit (about the cost of one strip)
 
 struct Params {
@@ -53,10 +60,9 @@ struct Params {
   double* rowpart;   // (warps + mB + 1) x 64 : slot (g + b) = row sums of warp g over block row b
   double* colpart;   // mB x n : colpart[I*n + c] = sum over rows of block I of A[r,c] v[r]
   double* abuf;      // 2 x n  : updated column (double-buffered by column parity)
-  double* wt;        // n      : w before the final alpha correction
   double* pvec;      // chunks x 2 NB : partial W^T v and V^T v per chunk of DOT_CHUNK rows
   unsigned long long* slots;  // 4 MAX_GRID words of per-CTA partials (double-buffered) + arrival counter + generation flag
-  long long* prof;   // optional cycle counters (null = off): [0..15] phases of CTA 0, [16 + cta] phase 3
+  long long* prof;   // optional cycle counters (null = off): [0..15] phases of CTA 0, [16 + cta] product phase
   int mB;            // ceil(n / 64)
 };
 
@@ -72,7 +78,7 @@ __device__ __forceinline__ double warp_sum_fixed(double v) {
 // generation flag; bar.sync extends both to the whole CTA).  All CTAs are co-resident (cooperative
 // launch); the arrival counter is monotonic within a launch.
 __device__ __forceinline__ void grid_allreduce2(unsigned long long* slots, unsigned nblocks, unsigned& gen, double& v0,
-                                                double& v1, double* s_a, double* s_b, double* s_out) {
+                                                double& v1, double* s_out) {
   const unsigned tid = threadIdx.x;
   ++gen;
   double* part = reinterpret_cast<double*>(slots) + (size_t)(gen & 1u) * MAX_GRID * 2;  // double-buffered partials
@@ -81,17 +87,14 @@ __device__ __forceinline__ void grid_allreduce2(unsigned long long* slots, unsig
   if (tid == 0) {
     part[2 * blockIdx.x] = v0;
     part[2 * blockIdx.x + 1] = v1;
-    unsigned ticket;
-    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(bar) : "memory");
-    if (ticket == gen * nblocks - 1u) {
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen) : "memory");
-    } else {
-      unsigned spins = 0, seen;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar + 1) : "memory");
-        if (++spins > (1u << 25)) __trap();  // never hang the device
-      } while (seen < gen);
-    }
+    // fire-and-forget arrival, then poll the counter itself (one hop less than ticket + flag)
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    const unsigned target = gen * nblocks;
+    unsigned spins = 0, seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+      if (++spins > (1u << 25)) __trap();  // never hang the device
+    } while (seen < target);
   }
   __syncthreads();
   if (tid < 32) {
@@ -107,8 +110,6 @@ __device__ __forceinline__ void grid_allreduce2(unsigned long long* slots, unsig
   __syncthreads();
   v0 = s_out[0];
   v1 = s_out[1];
-  (void)s_a;
-  (void)s_b;
 }
 
 // CTA-wide sum of two values; result valid in thread 0.
@@ -116,6 +117,7 @@ __device__ __forceinline__ void cta_reduce2(double& a, double& b, double* s_tmp 
   a = warp_sum_fixed(a);
   b = warp_sum_fixed(b);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();  // s_tmp may still be read from the previous use
   if (l == 0) { s_tmp[w] = a; s_tmp[16 + w] = b; }
   __syncthreads();
   if (threadIdx.x < 32) {
@@ -156,8 +158,8 @@ __device__ __forceinline__ double butterfly16(double (&p)[16], int lane) {
   return r;
 }
 
-// Work units of phase 3, in this order: the strips of block row b = 0, 1, ... (block row b has
-// SPT (b + 1) strips, the first at unit SPT b (b + 1) / 2), then the panel dot-product chunks.
+// Work units of the product phase, in this order: the strips of block row b = 0, 1, ... (block row b
+// has SPT (b + 1) strips, the first at unit SPT b (b + 1) / 2), then the panel dot-product chunks.
 // Unit u belongs to warp owner(u) = floor(u * nw / total) with nw = min(warps, total): contiguous
 // runs, equal to within one unit, and every warp below nw owns at least one unit.
 struct UnitMap {
@@ -167,11 +169,60 @@ struct UnitMap {
   __device__ __forceinline__ long long owner(long long u) const { return u * nw / total; }
 };
 
+// Row i of the row phase, stage 1: V(i, t), W(i, t) for t = sub + u TPR < jj into vv / ww, and this
+// lane's share of y(i) (the row and column partial sums of the product phase).  No dependence on the
+// panel dot products, so these loads overlap their reduction.
+__device__ __forceinline__ double row_load(const Params& P, const UnitMap& um, int i, bool live, int sub, int jj, int Bmin,
+                                           double (&vv)[RPT], double (&ww)[RPT]) {
+  const int n = P.n;
+#pragma unroll
+  for (int u = 0; u < RPT; ++u) {
+    const int t = sub + u * TPR;
+    const bool on = live && t < jj;
+    vv[u] = on ? P.A[i + (long long)(P.j0 + t) * P.lda] : 0.0;
+    ww[u] = on ? P.W[i + (long long)t * n] : 0.0;
+  }
+  double acc = 0;
+  if (live) {
+    // row parts: the warps whose runs intersect block row b, slot (g + b); column parts: block rows Ii..mB-1
+    const int Ii = i / TILE, b = Ii - Bmin;
+    const long long s0 = um.first_of_row(b);
+    const int g0 = (int)um.owner(s0), g1 = (int)um.owner(s0 + (long long)SPT * (b + 1) - 1);
+    const int nrow = g1 - g0 + 1, ncol = P.mB - Ii;
+    const double* rp = P.rowpart + (size_t)(g0 + b) * TILE + (i - Ii * TILE);
+    const double* cp = P.colpart + ((long long)(Ii - nrow) * n + i);  // k >= nrow -> block row Ii + (k - nrow)
+    const int ntot = nrow + ncol;
+    for (int k0 = sub; k0 < ntot; k0 += TPR * KB) {  // KB loads in flight per lane
+      double t[KB];
+#pragma unroll
+      for (int q = 0; q < KB; ++q) {
+        const int k = k0 + q * TPR;
+        t[q] = (k < ntot) ? ((k < nrow) ? rp[(size_t)k * TILE] : cp[(size_t)k * n]) : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < KB; ++q) acc += t[q];
+    }
+  }
+  return acc;
+}
+// stage 2: y(i) - (V p1)(i) - (W p2)(i), summed over the TPR lanes of the row (all lanes of the warp call)
+__device__ __forceinline__ double row_combine(double acc, int sub, int jj, const double* s_p1, const double* s_p2,
+                                              const double (&vv)[RPT], const double (&ww)[RPT]) {
+#pragma unroll
+  for (int u = 0; u < RPT; ++u) {
+    const int t = sub + u * TPR;
+    if (t < jj) acc -= vv[u] * s_p1[t] + ww[u] * s_p2[t];
+  }
+#pragma unroll
+  for (int o = 1; o < TPR; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
 __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
-  __shared__ double s_tmp[32];
-  __shared__ double s_ra[MAX_GRID], s_rb[MAX_GRID], s_out[2];  // grid all-reduce staging
-  __shared__ double s_p1[NB], s_p2[NB];                        // W^T v, V^T v (phase 4)
-  __shared__ double s_vj[THREADS / 32][SW];                    // per-warp copy of v over the strip's columns
+  __shared__ double s_tmp[32], s_out[2], s_bc[2];
+  __shared__ double s_p1[NB], s_p2[NB];      // W^T v, V^T v
+  __shared__ double s_vr[NB], s_wr[NB];      // row j+1 of V and W
+  __shared__ double s_vj[THREADS / 32][SW];  // per-warp copy of v over the strip's columns
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned nblocks = gridDim.x;
@@ -184,74 +235,41 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
 
   const int gthreads = nblocks * THREADS;
   const int gtid = blockIdx.x * THREADS + tid;
-  const int slot = gtid / TPR, sub = gtid % TPR, nslots = gthreads / TPR;
+  // row phase: warps 0..ROW_WARPS-1 sweep rows (TPR lanes per row), the last warp recomputes row j+1
+  const int sub = lane % TPR;
+  const int slot = blockIdx.x * ROWS_PER_CTA + warp * (32 / TPR) + lane / TPR, nslots = nblocks * ROWS_PER_CTA;
+  const bool row_warp = warp < ROW_WARPS;
   const int gwarp = blockIdx.x * (THREADS / 32) + warp;
   const long long nwarps = (long long)nblocks * (THREADS / 32);
-
-  double tau_prev = 0, scale_prev = 0, alpha2_prev = 0;  // of column j-1 (uniform across the grid)
 
   const bool prof = P.prof != nullptr && blockIdx.x == 0 && tid == 0;
   long long tc = prof ? clock64() : 0;
 #define RS_PROF(k) if (prof) { const long long t_ = clock64(); P.prof[k] += t_ - tc; tc = t_; }
+
+  // ---------------- first column of the panel: nothing to apply yet -----------------------------
+  double ss = 0, alpha_part = 0;
+  {
+    const int j = P.j0;
+    double* ab = P.abuf + (size_t)(j & 1) * n;
+    for (int i = j + gtid; i < n; i += gthreads) {
+      const double a = A[i + (long long)j * lda];
+      ab[i] = a;
+      if (i == j) P.d[j] = a;
+      else if (i == j + 1) alpha_part = a;
+      else ss += a * a;
+    }
+  }
+
   for (int jj = 0; jj < P.pw; ++jj) {
     const int j = P.j0 + jj;
-    double* ab = P.abuf + (size_t)(j & 1) * n;               // this column, updated
-    const double* abp = P.abuf + (size_t)((j - 1) & 1) * n;  // previous column (gives v_{j-1})
+    const double* ab = P.abuf + (size_t)(j & 1) * n;      // this column, updated
+    double* abn = P.abuf + (size_t)((j + 1) & 1) * n;     // next column
 
-    // ---------------- phase 1: finish W(:, jj-1), update column j, norm of its tail ------------
-    // a(i) = A(i,j) - sum_t V(i,t) W(j,t) + W(i,t) V(j,t); every load of a row is issued in one batch.
-    double ss = 0, alpha_part = 0;
-    for (int base = j; base < n; base += nslots) {  // trip count uniform across the grid (shuffles below)
-      const int i = base + slot;
-      const bool live = i < n;
-      const double a_ij = (live && sub == 0) ? A[i + (long long)j * lda] : 0.0;
-      double wlast_i = 0, wlast_j = 0;
-      if (live && jj > 0) {
-        const double vprev = (i == j) ? 1.0 : abp[i] * scale_prev;
-        wlast_i = P.wt[i] + alpha2_prev * vprev;  // final value of W(i, jj-1)
-        wlast_j = P.wt[j] + alpha2_prev;          // final value of W(j, jj-1)   (v_{j-1}(j) = 1)
-      }
-      double vi[RPT], wi[RPT], vj[RPT], wj[RPT];
-#pragma unroll
-      for (int u = 0; u < RPT; ++u) {
-        const int t = sub + u * TPR;
-        const bool on = live && t < jj;
-        const bool old = on && t != jj - 1;
-        vi[u] = on ? A[i + (long long)(P.j0 + t) * lda] : 0.0;
-        vj[u] = on ? A[j + (long long)(P.j0 + t) * lda] : 0.0;
-        wi[u] = old ? W[i + (long long)t * ldw] : 0.0;
-        wj[u] = old ? W[j + (long long)t * ldw] : 0.0;
-      }
-      double acc = 0;
-#pragma unroll
-      for (int u = 0; u < RPT; ++u) {
-        const int t = sub + u * TPR;
-        if (live && t < jj) {
-          double wit = wi[u], wjt = wj[u];
-          if (t == jj - 1) {
-            wit = wlast_i;
-            wjt = wlast_j;
-            W[i + (long long)t * ldw] = wit;
-          }
-          acc += vi[u] * wjt + wit * vj[u];
-        }
-      }
-#pragma unroll
-      for (int o = 1; o < TPR; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (sub == 0 && live) {
-        const double a = a_ij - acc;
-        ab[i] = a;
-        if (i == j) P.d[j] = a;
-        else if (i == j + 1) alpha_part = a;
-        else ss += a * a;
-      }
-    }
-    RS_PROF(0)
     cta_reduce2(ss, alpha_part, s_tmp);
-    grid_allreduce2(P.slots, nblocks, gen, ss, alpha_part, s_ra, s_rb, s_out);  // #1: ||x||^2 and alpha
+    grid_allreduce2(P.slots, nblocks, gen, ss, alpha_part, s_out);  // #1: ||x||^2 and alpha
     RS_PROF(1)
 
-    // ---------------- phase 2: reflector (every thread, identical arithmetic) -------------------
+    // ---------------- reflector (every thread, identical arithmetic) ----------------------------
     double tau = 0, scale = 0;
     {
       const double alpha = alpha_part, xn2 = ss;
@@ -266,7 +284,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
     // store v in the matrix (owners only; readers use ab[] * scale)
     for (int i = j + 1 + gtid; i < n; i += gthreads) A[i + (long long)j * lda] = (i == j + 1) ? 1.0 : ab[i] * scale;
 
-    // ---------------- phase 3: y = A22 v over the lower triangle; panel dot products ------------
+    // ---------------- product phase: y = A22 v over the lower triangle; panel dot products -------
     const long long t3 = (P.prof != nullptr && tid == 0) ? clock64() : 0;
     const int Bmin = (j + 1) / TILE;
     const int mt = P.mB - Bmin;
@@ -275,6 +293,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
     um.strips = um.first_of_row(mt);
     um.total = um.strips + 2LL * jj * nch;
     um.nw = nwarps < um.total ? nwarps : um.total;
+    double yv = 0;  // this lane's share of v^T A22 v
     if (gwarp < um.nw) {
       long long u = um.start(gwarp);
       const long long uend = um.start(gwarp + 1);
@@ -308,11 +327,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
             vi1 = (ok1 && r1i > j) ? (r1i == j + 1 ? 1.0 : ab[r1i] * scale) : 0.0;
             newrow = false;
           }
+          double vcol;  // v at column cbase + (lane & 15)
           {
             const int c = cbase + (lane & (SW - 1));
-            const double v = (c < n && c > j) ? (c == j + 1 ? 1.0 : ab[c] * scale) : 0.0;
+            vcol = (c < n && c > j) ? (c == j + 1 ? 1.0 : ab[c] * scale) : 0.0;
             __syncwarp();
-            if (lane < SW) s_vj[warp][lane] = v;
+            if (lane < SW) s_vj[warp][lane] = vcol;
             __syncwarp();
           }
           if (I != J) {
@@ -341,8 +361,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
           }
           const double cs = butterfly16(p, lane);
           if (!(lane & 1)) {
-            const int cg = cbase + ((lane >> 1) & 15);
+            const int cl = (lane >> 1) & 15;
+            const int cg = cbase + cl;
             if (cg < n) P.colpart[(size_t)I * n + cg] = cs;
+            yv += cs * s_vj[warp][cl];
           }
           // advance; flush the row sums at the end of a block row or of the run
           ++k;
@@ -351,6 +373,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
             double* rp = P.rowpart + (size_t)(gwarp + b) * TILE;
             rp[lane] = rs0;
             rp[lane + 32] = rs1;
+            yv += rs0 * vi0 + rs1 * vi1;
             rs0 = rs1 = 0;
           }
           if (endrow) { ++b; k = 0; newrow = true; }
@@ -376,90 +399,95 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
     RS_PROF(2)
     if (P.prof != nullptr && tid == 0) { P.prof[16 + blockIdx.x] += clock64() - t3; }
     {
-      double z0 = 0, z1 = 0;
-      grid_allreduce2(P.slots, nblocks, gen, z0, z1, s_ra, s_rb, s_out);  // #2: plain barrier
+      double z1 = 0;
+      cta_reduce2(yv, z1, s_tmp);
+      grid_allreduce2(P.slots, nblocks, gen, yv, z1, s_out);  // #2: v^T A22 v
     }
     RS_PROF(3)
 
-    // ---------------- phase 4: w = tau (y - V p1 - W p2), partial w.v -----------------------------
-    double dotp = 0;
-    bool first = true;
-    for (int base = j + 1; base < n; base += nslots) {
-      const int i = base + slot;
-      const bool live = i < n;
-      const int Ii = i / TILE, b = Ii - Bmin;
-      double vv[RPT], ww[RPT];
+    // ---------------- row phase: w, final W(:, jj), and the update of column j + 1 ---------------
+    // One memory round trip: every warp first issues the loads of its row (the last warp: row j+1, whose
+    // w every CTA needs, recomputed with the owner's arithmetic) and of the partial panel dot products.
+    const bool more = jj + 1 < P.pw;
+    double pa = 0;
+    {
+      const int q = tid >> 2, c4 = tid & 3;
+      if (q < 2 * jj)
+        for (int ch = c4; ch < nch; ch += 4) pa += P.pvec[(size_t)ch * (2 * NB) + q];
+    }
+    int i = row_warp ? j + 1 + slot : j + 1;
+    bool live = i < n;
+    double a_next = (row_warp && live && more && sub == 0) ? A[i + (long long)(j + 1) * lda] : 0.0;
+    double vi = live ? ((i == j + 1) ? 1.0 : ab[i] * scale) : 0.0;
+    double vv[RPT], ww[RPT];
+    double acc = row_load(P, um, i, live, sub, jj, Bmin, vv, ww);
+    {
+      const int q = tid >> 2, c4 = tid & 3;
+      pa += __shfl_xor_sync(0xffffffffu, pa, 1);
+      pa += __shfl_xor_sync(0xffffffffu, pa, 2);
+      if (c4 == 0 && q < 2 * jj) {
+        if (q < jj) s_p1[q] = pa;
+        else s_p2[q - jj] = pa;
+      }
+    }
+    if (!row_warp && lane < TPR) {
 #pragma unroll
-      for (int u = 0; u < RPT; ++u) {
-        const int t = sub + u * TPR;
-        const bool on = live && t < jj;
-        vv[u] = on ? A[i + (long long)(P.j0 + t) * lda] : 0.0;
-        ww[u] = on ? W[i + (long long)t * ldw] : 0.0;
-      }
-      double acc = 0;
-      if (live) {
-        // row parts: the warps whose runs intersect block row b, slot (g + b); column parts: block rows Ii..mB-1
-        const long long s0 = um.first_of_row(b);
-        const int g0 = (int)um.owner(s0), g1 = (int)um.owner(s0 + (long long)SPT * (b + 1) - 1);
-        const int nrow = g1 - g0 + 1, ncol = P.mB - Ii;
-        const double* rp = P.rowpart + (size_t)(g0 + b) * TILE + (i - Ii * TILE);
-        const double* cp = P.colpart + ((long long)(Ii - nrow) * n + i);  // k >= nrow -> block row Ii + (k - nrow)
-        const int ntot = nrow + ncol;
-#pragma unroll 8
-        for (int k = sub; k < ntot; k += TPR) acc += (k < nrow) ? rp[(size_t)k * TILE] : cp[(size_t)k * n];
-      }
-      if (first) {
-        // panel dot products: sum the row chunks (4 threads per product), overlapped with the loads above
-        first = false;
-        const int q = tid >> 2, c4 = tid & 3;
-        double pa = 0;
-        if (q < 2 * jj)
-          for (int ch = c4; ch < nch; ch += 4) pa += P.pvec[(size_t)ch * (2 * NB) + q];
-        pa += __shfl_xor_sync(0xffffffffu, pa, 1);
-        pa += __shfl_xor_sync(0xffffffffu, pa, 2);
-        if (c4 == 0 && q < 2 * jj) {
-          if (q < jj) s_p1[q] = pa;
-          else s_p2[q - jj] = pa;
+      for (int u = 0; u < RPT; ++u) { s_vr[sub + u * TPR] = vv[u]; s_wr[sub + u * TPR] = ww[u]; }  // zero where t >= jj
+    }
+    __syncthreads();
+    RS_PROF(5)
+    acc = row_combine(acc, sub, jj, s_p1, s_p2, vv, ww);
+    double upd = 0;
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) upd += vv[u] * s_wr[sub + u * TPR] + ww[u] * s_vr[sub + u * TPR];
+#pragma unroll
+    for (int o = 1; o < TPR; o <<= 1) upd += __shfl_xor_sync(0xffffffffu, upd, o);
+    if (!row_warp) {
+      // w^T v = tau (v^T A22 v - 2 p1.p2)  -> alpha2;  w(j+1) before the correction
+      double pp = 0;
+      for (int t = lane; t < jj; t += 32) pp += s_p1[t] * s_p2[t];
+      pp = warp_sum_fixed(pp);
+      const double wv = tau * (yv - 2.0 * pp);
+      if (lane == 0) { s_bc[0] = -0.5 * tau * wv; s_bc[1] = tau * acc; }
+    }
+    __syncthreads();
+    RS_PROF(6)
+    const double alpha2 = s_bc[0];
+    const double wj1 = s_bc[1] + alpha2;  // final W(j+1, jj)   (v(j+1) = 1)
+    ss = 0;
+    alpha_part = 0;
+    if (row_warp) {
+      for (int base = j + 1;;) {  // trip count uniform within the warp (shuffles inside)
+        if (sub == 0 && live) {
+          const double wi = tau * acc + alpha2 * vi;  // final W(i, jj)
+          W[i + (long long)jj * ldw] = wi;
+          if (more) {
+            // A(i, j+1) - sum_{t <= jj} V(i,t) W(j+1,t) + W(i,t) V(j+1,t)   with V(j+1, jj) = 1
+            const double a = a_next - upd - (vi * wj1 + wi);
+            abn[i] = a;
+            if (i == j + 1) P.d[j + 1] = a;
+            else if (i == j + 2) alpha_part = a;
+            else ss += a * a;
+          }
         }
-        __syncthreads();
-      }
+        base += nslots;
+        if (base >= n) break;
+        i = base + slot;
+        live = i < n;
+        a_next = (live && more && sub == 0) ? A[i + (long long)(j + 1) * lda] : 0.0;
+        vi = live ? ab[i] * scale : 0.0;
+        acc = row_load(P, um, i, live, sub, jj, Bmin, vv, ww);
+        acc = row_combine(acc, sub, jj, s_p1, s_p2, vv, ww);
+        upd = 0;
 #pragma unroll
-      for (int u = 0; u < RPT; ++u) {
-        const int t = sub + u * TPR;
-        if (live && t < jj) acc -= vv[u] * s_p1[t] + ww[u] * s_p2[t];
-      }
+        for (int u = 0; u < RPT; ++u) upd += vv[u] * s_wr[sub + u * TPR] + ww[u] * s_vr[sub + u * TPR];
 #pragma unroll
-      for (int o = 1; o < TPR; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (sub == 0 && live) {
-        const double wi = tau * acc;
-        P.wt[i] = wi;
-        const double vi = (i == j + 1) ? 1.0 : ab[i] * scale;
-        dotp += wi * vi;
+        for (int o = 1; o < TPR; o <<= 1) upd += __shfl_xor_sync(0xffffffffu, upd, o);
       }
     }
     RS_PROF(4)
-    {
-      double z = 0;
-      cta_reduce2(dotp, z, s_tmp);
-      grid_allreduce2(P.slots, nblocks, gen, dotp, z, s_ra, s_rb, s_out);  // #3: w.v
-    }
-    alpha2_prev = -0.5 * tau * dotp;
-    tau_prev = tau;
-    scale_prev = scale;
-    RS_PROF(5)
   }
 #undef RS_PROF
-
-  // final correction of the last panel column
-  {
-    const int jj = P.pw - 1, j = P.j0 + jj;
-    const double* ab = P.abuf + (size_t)(j & 1) * n;
-    for (int i = j + 1 + gtid; i < n; i += gthreads) {
-      const double vi = (i == j + 1) ? 1.0 : ab[i] * scale_prev;
-      W[i + (long long)jj * ldw] = P.wt[i] + alpha2_prev * vi;
-    }
-  }
-  (void)tau_prev;
 }
 
 __global__ void k_restore_subdiag(double* A, long long lda, int n, const double* e, double* d) {
@@ -474,8 +502,7 @@ inline size_t rowpart_doubles(int64_t n) {
 }
 inline size_t workspace_doubles(int64_t n) {
   const int64_t mB = (n + TILE - 1) / TILE;
-  return (size_t)n * NB + rowpart_doubles(n) + (size_t)mB * n + 2 * n + n + 2 * NB * (n / DOT_CHUNK + 1) +
-         4 * MAX_GRID + 8 + 64;
+  return (size_t)n * NB + rowpart_doubles(n) + (size_t)mB * n + 2 * n + 2 * NB * (n / DOT_CHUNK + 1) + 4 * MAX_GRID + 8 + 64;
 }
 
 // A: n x n column-major, lower triangle referenced.  work: workspace_doubles(n) doubles (256-byte aligned).
@@ -495,7 +522,6 @@ inline cudaError_t run(cublasHandle_t blas, cudaStream_t stream, double* A, int6
   P.rowpart = w;  w += rowpart_doubles(n);
   P.colpart = w;  w += (size_t)mB * n;
   P.abuf = w;     w += 2 * n;
-  P.wt = w;       w += n;
   P.pvec = w;     w += 2 * NB * (n / DOT_CHUNK + 1);
   P.slots = reinterpret_cast<unsigned long long*>(w);
   P.prof = prof;
@@ -503,7 +529,7 @@ inline cudaError_t run(cublasHandle_t blas, cudaStream_t stream, double* A, int6
   for (int64_t j0 = 0; j0 < n - 1; j0 += NB) {
     const int pw = (int)((n - 1 - j0) < NB ? (n - 1 - j0) : NB);
     P.j0 = (int)j0; P.pw = pw;
-    // generation numbers restart at 1 in every launch: clear the flags
+    // generation numbers restart at 1 in every launch: clear the counter and the flag
     cudaError_t st = cudaMemsetAsync(P.slots, 0, sizeof(unsigned long long) * (4 * MAX_GRID + 8), stream);
     if (st != cudaSuccess) return st;
     void* args[] = {&P};

@@ -108,9 +108,9 @@ int main(int argc, char** argv) {
   if (prof) {
     long long h[1100];
     CK(cudaMemcpy(h, prof, 8 * 1100, cudaMemcpyDeviceToHost));
-    const char* names[6] = {"phase1 (column update)", "allreduce1 (norm, alpha)", "phase2+3 (reflector, symv)", "barrier2",
-                            "phase4 (combine)", "allreduce3 (w.v)"};
-    for (int k = 0; k < 6; ++k)
+    const char* names[7] = {"(unused)", "allreduce1 (norm, alpha)", "reflector + product phase", "allreduce2 (v^T A v)",
+                            "row phase c (row loop)", "row phase a (panel dots)", "row phase b (w(j+1), alpha2)"};
+    for (int k = 0; k < 7; ++k)
       printf("  prof %-28s %8.2f ms total over %d reps (cycles/1.9GHz)  %.2f us/column\n", names[k], h[k] / 1.9e6, reps,
              h[k] / 1.9e3 / reps / (double)n);
   }
