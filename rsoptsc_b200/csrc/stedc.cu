@@ -10,7 +10,7 @@
 //     Loewner weights     one warp per pole
 //     M = R S             the k x k eigenvectors of D + rho z z^T scattered straight into the n_m x n_m
 //                         update matrix (deflated columns = unit vectors, Givens rotations as row
-//                         operations), so that the whole merge is ONE GEMM  Q_out = Q_in M
+//                         operations), so that the whole merge is Q_out = diag(Q1, Q2) M: two GEMMs
 //     GEMM                tcgen05 split-integer FP64-equivalent GEMM (gemm_ozaki.cu) for blocks of
 //                         1536 rows and more, cuBLAS below
 //
@@ -347,7 +347,10 @@ void stedc_device(const double* d_d, const double* d_e, int64_t n64, double* d_l
       if (nd > 0) RS_LAUNCH(k_set_ones, (unsigned)cdiv(nd, 256), 256, 0, nd, nm, p_idx_def, p_pos_def, M);
       if (nrot > 0)
         RS_LAUNCH(k_rot_rows, (unsigned)cdiv(nm, 128), 128, 0, nm, (const Rotation*)(dv_pack.p + offs[m].rots), nrot, M);
-      gemm_nn_ld(Qblk, ldq, M, nm, Qout, ldq, nm, nm, nm);
+      // Q_in is block diagonal (the two children): two half-height GEMMs instead of one full one
+      const int n1 = blocks[2 * m].size, n2 = nm - n1;
+      gemm_nn_ld(Qblk, ldq, M, nm, Qout, ldq, n1, nm, n1);
+      gemm_nn_ld(Qblk + n1 + (long long)n1 * ldq, ldq, M + n1, nm, Qout + n1, ldq, n2, nm, n2);
     }
     std::vector<Block> next;
     for (size_t m = 0; m < nmerge; ++m) next.push_back({blocks[2 * m].off, blocks[2 * m].size + blocks[2 * m + 1].size});

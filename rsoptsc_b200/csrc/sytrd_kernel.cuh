@@ -46,6 +46,7 @@ constexpr int RPT = NB / TPR;   // panel columns per thread in the row-wise phas
 constexpr int KB = 24;          // partial sums of a row fetched per lane in one batch
 constexpr int ROW_WARPS = THREADS / 32 - 1;        // warps that sweep rows; the last warp handles row j+1
 constexpr int ROWS_PER_CTA = ROW_WARPS * (32 / TPR);
+constexpr int L2_BLOCK_ROWS = 0;  // plain (L2-allocating) loads below this many block rows: measured no gain on B200, off
 constexpr int DOT_CHUNK = 512;  // rows per panel dot-product unit (about the cost of one strip)
 
 struct Params {
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
     um.total = um.strips + 2LL * jj * nch;
     um.nw = nwarps < um.total ? nwarps : um.total;
     double yv = 0;  // this lane's share of v^T A22 v
+    const bool stream_loads = mt > L2_BLOCK_ROWS;
     if (gwarp < um.nw) {
       long long u = um.start(gwarp);
       const long long uend = um.start(gwarp + 1);
@@ -319,8 +321,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
           for (int c = 0; c < SW; ++c) {
             const bool okc = cbase + c < n;
             const double* col = Ab + (long long)c * lda;
-            a0[c] = (ok0 && okc) ? __ldcs(col + r0i) : 0.0;  // streaming: do not evict the panel from L2
-            a1[c] = (ok1 && okc) ? __ldcs(col + r1i) : 0.0;
+            // streaming loads (do not evict the panel from L2) while the triangle exceeds L2; plain
+            // loads once it fits, so that the tail of the factorisation runs out of L2
+            if (stream_loads) {
+              a0[c] = (ok0 && okc) ? __ldcs(col + r0i) : 0.0;
+              a1[c] = (ok1 && okc) ? __ldcs(col + r1i) : 0.0;
+            } else {
+              a0[c] = (ok0 && okc) ? col[r0i] : 0.0;
+              a1[c] = (ok1 && okc) ? col[r1i] : 0.0;
+            }
           }
           if (newrow) {
             vi0 = (ok0 && r0i > j) ? (r0i == j + 1 ? 1.0 : ab[r0i] * scale) : 0.0;

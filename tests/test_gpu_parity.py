@@ -494,3 +494,74 @@ def test_computeM_with_both_gemm_backends(backend):
         lib.rsoptsc_set_gemm_backend(prev)
     assert got["iters"] == ref["iters"]
     assert relF(got["Z"], ref["Z"]) < 1e-6
+
+
+# ---- native symmetric eigensolver (sytrd_kernel.cuh + stedc.cu) vs the library solver ---------------
+def _sym_eig(G, solver):
+    import ctypes as C
+    from rsoptsc_b200 import _lib
+    lib = _lib.load()
+    dp = C.POINTER(C.c_double)
+    n = G.shape[0]
+    Gf = np.asfortranarray(G, dtype=np.float64)
+    lam = np.zeros(n)
+    V = np.zeros((n, n), order="F")
+    _lib.check(lib.rsoptsc_debug_sym_eig(Gf.ctypes.data_as(dp), n, solver, lam.ctypes.data_as(dp),
+                                         V.ctypes.data_as(dp), 1, None))
+    return lam, V
+
+
+def _gram_like(n, rng, K=30):
+    Z = np.zeros((n, n))
+    for i in range(n):
+        Z[rng.choice(n, K, replace=False), i] = rng.random(K) / K
+    return Z.T @ Z
+
+
+@pytest.mark.parametrize("n,kind", [(65, "random"), (257, "random"), (700, "gram"), (1600, "gram"), (2300, "lowrank")])
+def test_native_eigensolver(n, kind):
+    """Own tridiagonalisation + tridiagonal divide and conquer + library back-transformation: eigenvalues
+    agree with cuSOLVER to rounding, eigenvectors orthonormal, residual at rounding level."""
+    rng = np.random.default_rng(n)
+    if kind == "random":
+        A = rng.standard_normal((n, n))
+        G = (A + A.T) / 2
+    elif kind == "gram":
+        G = _gram_like(n, rng)
+    else:  # numerically rank 40: one big cluster of tiny eigenvalues (heavy deflation)
+        B = rng.standard_normal((n, 40))
+        G = B @ B.T + 1e-10 * np.eye(n)
+    l0, _ = _sym_eig(G, 0)
+    l1, V1 = _sym_eig(G, 1)
+    scale = np.abs(l0).max()
+    assert np.all(np.diff(l1) >= 0)
+    assert np.abs(l1 - l0).max() <= 1e-13 * n * scale
+    assert np.abs(V1.T @ V1 - np.eye(n)).max() <= 1e-13 * n
+    assert np.abs(G @ V1 - V1 * l1).max() <= 1e-13 * n * scale
+
+
+def test_computeM_with_native_eigensolver():
+    """The whole ADMM with every SVT through the native eigensolver (RSOPTSC_EIG=native lowers its size
+    threshold to 256 rows; fresh process: the switch is read once)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from conftest import small_problem\n"
+        "from oracle import rsoptsc_oracle as O\n"
+        "from rsoptsc_b200 import api\n"
+        "p = small_problem(200, 600, seed=5)\n"
+        "ref = O.computeM(O.mask_from_idx(p['idx'], 600), p['X'], 0.5, literal=False)\n"
+        "api.timers(True)\n"
+        "got = api.computeM(None, p['X'], 0.5, idx=p['idx'])\n"
+        "rep = api.phase_report()\n"
+        "rel = np.linalg.norm(got['Z'] - ref['Z']) / np.linalg.norm(ref['Z'])\n"
+        "assert 'eig_sytrd' in rep and rep['eig_sytrd']['calls'] > 0, rep\n"
+        "assert got['iters'] == ref['iters'] and rel < 1e-6, (got['iters'], ref['iters'], rel)\n"
+        "print('native eig path ok', rel)\n" % (root, os.path.join(root, "tests")))
+    env = dict(os.environ, RSOPTSC_EIG="native")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "native eig path ok" in r.stdout, r.stdout + r.stderr
