@@ -155,6 +155,14 @@ def own_kernel_bytes(name, m, n, nnz):
     }.get(name)
 
 
+# ncu --set full of one k_latrd_panel launch (first panel of a 7,954-row block): filled from profiles/
+SYTRD_NCU_TRAFFIC = 17.32e9
+SYTRD_NCU_NOTE = ("dram read+write of ONE launch, the first 64-column panel of a 7,954-row block, from ncu --set full "
+                  "(profiles/r1_latrd_panel_ncu_full.csv): 17.14 GB read + 0.18 GB written against 16.06 GB algorithmic "
+                  "(lower triangles of the 64 trailing matrices) = 1.08x; 4.78 TB/s DRAM read rate over the launch; the "
+                  "rest of the time is the two grid synchronisations and the row phase of every column")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -223,6 +231,7 @@ def main():
     phases = api.phase_report()
     oz_flops = _lib.load().rsoptsc_counter(b"ozaki_fp64_flops")
     oz_iops = _lib.load().rsoptsc_counter(b"ozaki_int8_ops")
+    sytrd_bytes = _lib.load().rsoptsc_counter(b"sytrd_panel_bytes")
     api.timers(False)
 
     # end to end through the host-buffer C ABI, pinned host input/output
@@ -273,7 +282,29 @@ def main():
         own = [(p, v) for p, v in phases.items() if own_kernel_bytes(p, m, n, nnz)]
         roof = None
         oz = phases.get("ozaki_gemm")
-        if oz and oz["ms"] > 0:
+        sy = phases.get("sytrd_panel")
+        if sy and sy["ms"] > 0 and (not oz or sy["ms"] >= oz["ms"]):
+            # dominant kernel: the cooperative panel kernel of the tridiagonalisation (symmetric
+            # eigensolver of every SVT).  HBM-bound: its product phase reads the lower triangle of the
+            # trailing matrix once per column; algorithmic bytes = sum over columns of 4 (n - j - 1)^2.
+            secs = sy["ms"] / 1e3
+            achieved = sytrd_bytes / secs / 1e9
+            roof = {"kernel": "k_latrd_panel (Householder tridiagonalisation, 64-column panels)", "bound": "hbm",
+                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": SYTRD_NCU_TRAFFIC,
+                    "traffic_note": SYTRD_NCU_NOTE,
+                    "peak_source": peak_src, "share_of_step": secs / t_dev, "launches": sy["calls"],
+                    "algorithmic_bytes_per_launch": sytrd_bytes / max(sy["calls"], 1)}
+            if oz and oz["ms"] > 0:
+                bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
+                pairs = max(oz_iops / max(oz_flops, 1.0), 1.0)
+                osec = oz["ms"] / 1e3
+                roof["second_kernel"] = {
+                    "kernel": "k_ozaki_gemm<8> (tcgen05.mma kind::i8, FP64-equivalent)", "bound": "tensor",
+                    "achieved": oz_flops / osec / 1e12, "peak": 2.0 * bf16 / pairs, "unit": "TFLOP/s",
+                    "frac": (oz_flops / osec / 1e12) / (2.0 * bf16 / pairs), "share_of_step": osec / t_dev,
+                    "launches": oz["calls"], "cublas_fp64_reference_tflops": 35.6}
+        elif oz and oz["ms"] > 0:
             # dominant kernel this repo owns: the tcgen05 kind::i8 split-integer GEMM (Gram + the two
             # reconstruction GEMMs of every SVT).  achieved = FP64-equivalent flops / device time;
             # peak = int8 tensor peak (2 x measured dense bf16) / 36 slice-pair MMAs per FP64 MAC.

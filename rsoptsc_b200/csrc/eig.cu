@@ -139,7 +139,18 @@ static void sym_eig_native(double* d_A, int64_t n, double* d_lam) {
     Phase ph("eig_sytrd");
     DevBuf<double> work(sytrd::workspace_doubles(n));
     int64_t launches = 0;
-    RS_CUDA(sytrd::run(c.cublas, c.stream, d_A, n, n, d.p, e.p, tau.p, work.p, &launches));
+    sytrd::Hooks hooks;
+    Phase* panel_phase = nullptr;
+    hooks.user = &panel_phase;
+    hooks.before = [](void* u, double bytes) {
+      add_counter("sytrd_panel_bytes", bytes);
+      *static_cast<Phase**>(u) = new Phase("sytrd_panel");
+    };
+    hooks.after = [](void* u) {
+      delete *static_cast<Phase**>(u);
+      *static_cast<Phase**>(u) = nullptr;
+    };
+    RS_CUDA(sytrd::run(c.cublas, c.stream, d_A, n, n, d.p, e.p, tau.p, work.p, &launches, nullptr, &hooks));
     g_launches.fetch_add(launches, std::memory_order_relaxed);
   }
   {

@@ -516,8 +516,13 @@ inline size_t workspace_doubles(int64_t n) {
 
 // A: n x n column-major, lower triangle referenced.  work: workspace_doubles(n) doubles (256-byte aligned).
 // Returns cudaSuccess or the failing status; launches counted in *launches.
+struct Hooks {  // optional instrumentation around every panel launch (phase timers of the library)
+  void (*before)(void* user, double algorithmic_bytes) = nullptr;
+  void (*after)(void* user) = nullptr;
+  void* user = nullptr;
+};
 inline cudaError_t run(cublasHandle_t blas, cudaStream_t stream, double* A, int64_t n, int64_t lda, double* d, double* e,
-                       double* tau, double* work, int64_t* launches, long long* prof = nullptr) {
+                       double* tau, double* work, int64_t* launches, long long* prof = nullptr, const Hooks* hooks = nullptr) {
   if (n < 1) return cudaSuccess;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -542,7 +547,13 @@ inline cudaError_t run(cublasHandle_t blas, cudaStream_t stream, double* A, int6
     cudaError_t st = cudaMemsetAsync(P.slots, 0, sizeof(unsigned long long) * (4 * MAX_GRID + 8), stream);
     if (st != cudaSuccess) return st;
     void* args[] = {&P};
+    if (hooks && hooks->before) {
+      double bytes = 0;  // lower triangle of every trailing matrix the panel multiplies with
+      for (int jj = 0; jj < pw; ++jj) { const double m = (double)(n - (j0 + jj) - 1); bytes += 4.0 * m * m; }
+      hooks->before(hooks->user, bytes);
+    }
     st = cudaLaunchCooperativeKernel((void*)k_latrd_panel, dim3(grid), dim3(THREADS), args, 0, stream);
+    if (hooks && hooks->after) hooks->after(hooks->user);
     if (st != cudaSuccess) return st;
     if (launches) ++*launches;
     const int64_t r0 = j0 + pw, nr = n - r0;  // trailing block
