@@ -707,7 +707,7 @@ int rsoptsc_debug_sym_eig(const double* A, int64_t n, int32_t solver, double* la
                           double* ms_out) {
   return guarded([&] {
     cudaStream_t s = ctx().stream;
-    RS_REQUIRE(A && lam_out && n >= 1 && n <= 32768 && reps >= 1 && (solver == 0 || solver == 1), "debug_sym_eig: bad arguments");
+    RS_REQUIRE(A && lam_out && n >= 1 && n <= 65535 && reps >= 1 && (solver == 0 || solver == 1), "debug_sym_eig: bad arguments");
     const size_t nn = (size_t)n * n;
     DevBuf<double> a0(nn), a(nn), lam(n);
     a0.upload(A, nn, s);

@@ -114,12 +114,12 @@ static void sym_eig_mg(double* d_A, int64_t n, double* d_lam, bool vectors) {
 }
 
 // ---- native solver: own tridiagonalisation (sytrd_kernel.cuh) + own tridiagonal divide and conquer
-// (stedc.cu, GEMMs on tcgen05) + the library's LAPACK-convention back-transformation (Dormtr) ----------
+// (stedc.cu, GEMMs on tcgen05) + own blocked back-transformation (backtransform.cu, GEMMs on tcgen05) ---
 void stedc_device(const double* d_d, const double* d_e, int64_t n, double* d_lam, double* d_Z, double* d_S1, double* d_S2);
 
 // RSOPTSC_EIG=cusolver forces the library path, RSOPTSC_EIG=native lowers the size threshold to 256
 // (parity tests); default: native from RSOPTSC_NATIVE_MIN_N rows (4000: below that cuSOLVER's lower per-column latency
-// wins, measured on B200: 4,000 rows 81 vs 84 ms, 5,000 rows 119 vs 145 ms, 7,954 rows 296 vs 437 ms) up to 32,768.
+// wins, measured on B200: 4,000 rows 81 vs 84 ms, 5,000 rows 119 vs 145 ms, 7,954 rows 296 vs 437 ms) up to 65,535.
 static int64_t native_min_n() {
   static int64_t t = -2;
   if (t == -2) {
@@ -159,19 +159,32 @@ static void sym_eig_native(double* d_A, int64_t n, double* d_lam) {
     stedc_device(d.p, e.p, n, d_lam, Z.p, S1.p, S2.p);
   }
   {
-    Phase ph("eig_ormtr");
-    int lwork = 0;
-    RS_CUSOLVER(cusolverDnDormtr_bufferSize(c.cusolver, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)n, (int)n,
-                                            d_A, (int)n, tau.p, Z.p, (int)n, &lwork));
-    DevBuf<double> work((size_t)std::max(lwork, 1));
-    DevBuf<int> info(1);
-    RS_CUSOLVER(cusolverDnDormtr(c.cusolver, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)n, (int)n, d_A, (int)n,
-                                 tau.p, Z.p, (int)n, work.p, lwork, info.p));
-    int hinfo = 0;
-    RS_CUDA(cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    Phase ph("eig_backtransform");
+    // cusolverDnDormtr (38 ms at 7,954 rows) is still ahead of the own blocked back-transformation (49 ms: its
+    // panel-shaped GEMMs run at ~33 TF/s-eq) but overflows its 32-bit workspace above 32,768 rows.
+    // RSOPTSC_BACKTRANSFORM=native|cusolver forces one of them (tests).
+    static int use_lib = -1;
+    if (use_lib < 0) {
+      const char* e = getenv("RSOPTSC_BACKTRANSFORM");
+      use_lib = (e && std::string(e) == "native") ? 0 : 1;
+    }
+    if (use_lib && n <= 32768) {
+      int lwork = 0;
+      RS_CUSOLVER(cusolverDnDormtr_bufferSize(c.cusolver, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)n, (int)n,
+                                              d_A, (int)n, tau.p, Z.p, (int)n, &lwork));
+      DevBuf<double> work((size_t)std::max(lwork, 1));
+      DevBuf<int> info(1);
+      RS_CUSOLVER(cusolverDnDormtr(c.cusolver, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)n, (int)n, d_A,
+                                   (int)n, tau.p, Z.p, (int)n, work.p, lwork, info.p));
+      int hinfo = 0;
+      RS_CUDA(cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+      RS_CUDA(cudaStreamSynchronize(c.stream));
+      RS_REQUIRE(hinfo == 0, "back-transformation failed (info=" + std::to_string(hinfo) + ")");
+    } else {
+      apply_q_left(d_A, n, tau.p, n, Z.p);
+    }
     RS_CUDA(cudaMemcpyAsync(d_A, Z.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, c.stream));
     RS_CUDA(cudaStreamSynchronize(c.stream));
-    RS_REQUIRE(hinfo == 0, "back-transformation failed (info=" + std::to_string(hinfo) + ")");
   }
 }
 
@@ -186,7 +199,7 @@ void sym_eig_select(double* d_A, int64_t n, double* d_lam, int solver) {
 // in d_lam.  Throws when the solver reports failure.
 void sym_eig(double* d_A, int64_t n, double* d_lam, bool vectors) {
   RS_REQUIRE(n >= 1, "sym_eig: empty matrix");
-  if (vectors && native_min_n() >= 0 && n >= native_min_n() && n <= 32768) return sym_eig_native(d_A, n, d_lam);
+  if (vectors && native_min_n() >= 0 && n >= native_min_n() && n <= 65535) return sym_eig_native(d_A, n, d_lam);
   sym_eig_library(d_A, n, d_lam, vectors);
 }
 

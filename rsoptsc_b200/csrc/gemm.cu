@@ -14,6 +14,10 @@ void ozaki_gemm_nn(const double* A, const double* B, double* C, int64_t M, int64
 void ozaki_gemm_nt(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
 void ozaki_gemm_nn_ld(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M,
                       int64_t N, int64_t K);
+void ozaki_gemm_nn_ld_acc(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M,
+                          int64_t N, int64_t K);
+void ozaki_gemm_tn_ld(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M,
+                      int64_t N, int64_t K);
 void ozaki_gemm_tn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
 
 static int g_backend = -1;  // 0 cublas, 1 ozaki
@@ -59,6 +63,28 @@ void gemm_nn_ld(const double* A, int64_t lda, const double* B, int64_t ldb, doub
   if (use_ozaki(M, N, K)) return ozaki_gemm_nn_ld(A, lda, B, ldb, C, ldc, M, N, K);
   const double one = 1.0, zero = 0.0;
   RS_CUBLAS(cublasDgemm(ctx().cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)M, (int)N, (int)K, &one, A, (int)lda, B, (int)ldb,
+                        &zero, C, (int)ldc));
+}
+// Panel-shaped contractions (one dimension a few hundred, the others thousands): the tensor-core path
+// pays as soon as the operand slicing is amortised.
+static bool use_ozaki_panel(int64_t M, int64_t N, int64_t K) {
+  const int b = gemm_backend();
+  if (b == 0 || M > 65535 || N > 65535) return false;
+  const int64_t mn = std::min(M, std::min(N, K));
+  return mn >= 256 && (double)M * (double)N * (double)K >= 1536.0 * 1536.0 * 1536.0;
+}
+void gemm_nn_ld_acc(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M,
+                    int64_t N, int64_t K) {
+  if (use_ozaki_panel(M, N, K)) return ozaki_gemm_nn_ld_acc(A, lda, B, ldb, C, ldc, M, N, K);
+  const double one = 1.0;
+  RS_CUBLAS(cublasDgemm(ctx().cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)M, (int)N, (int)K, &one, A, (int)lda, B, (int)ldb,
+                        &one, C, (int)ldc));
+}
+void gemm_tn_ld(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t N,
+                int64_t K) {
+  if (use_ozaki_panel(M, N, K)) return ozaki_gemm_tn_ld(A, lda, B, ldb, C, ldc, M, N, K);
+  const double one = 1.0, zero = 0.0;
+  RS_CUBLAS(cublasDgemm(ctx().cublas, CUBLAS_OP_T, CUBLAS_OP_N, (int)M, (int)N, (int)K, &one, A, (int)lda, B, (int)ldb,
                         &zero, C, (int)ldc));
 }
 void gemm_nt(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K) {

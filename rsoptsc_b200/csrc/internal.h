@@ -92,6 +92,8 @@ void tridiag_eig(std::vector<double>& d, std::vector<double>& e, std::vector<dou
 void sym_eig(double* d_A, int64_t n, double* d_lam, bool vectors);
 // same with eigenvectors, solver forced: 0 library (cuSOLVER), 1 native (sytrd_kernel.cuh + stedc.cu)
 void sym_eig_select(double* d_A, int64_t n, double* d_lam, int solver);
+// backtransform.cu: Z (n x n) <- Q Z, Q = product of the Householder reflectors stored by the tridiagonalisation
+void apply_q_left(const double* d_A, int64_t lda, const double* d_tau, int64_t n, double* d_Z);
 
 struct SvtWorkspace {
   int64_t n = 0;

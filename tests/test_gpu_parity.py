@@ -562,6 +562,7 @@ def test_computeM_with_native_eigensolver():
         "assert 'eig_sytrd' in rep and rep['eig_sytrd']['calls'] > 0, rep\n"
         "assert got['iters'] == ref['iters'] and rel < 1e-6, (got['iters'], ref['iters'], rel)\n"
         "print('native eig path ok', rel)\n" % (root, os.path.join(root, "tests")))
-    env = dict(os.environ, RSOPTSC_EIG="native")
+    # ... and the own blocked back-transformation instead of cusolverDnDormtr (the default below 32,768 rows)
+    env = dict(os.environ, RSOPTSC_EIG="native", RSOPTSC_BACKTRANSFORM="native")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "native eig path ok" in r.stdout, r.stdout + r.stderr
