@@ -39,7 +39,10 @@ constexpr int NB = 64;          // panel width
 constexpr int THREADS = 512;    // 16 warps per CTA, one CTA per SM
 constexpr int MAX_GRID = 512;   // upper bound on the cooperative grid
 constexpr int TILE = 64;        // block edge of the triangle (rows per strip)
-constexpr int SW = 16;          // strip width (columns)
+#ifndef RS_SYTRD_SW
+#define RS_SYTRD_SW 16
+#endif
+constexpr int SW = RS_SYTRD_SW;  // strip width (columns): 16 or 8
 constexpr int SPT = TILE / SW;  // strips per 64 x 64 block
 constexpr int TPR = 8;          // threads per row in the row-wise phase
 constexpr int RPT = NB / TPR;   // panel columns per thread in the row-wise phase
@@ -47,7 +50,7 @@ constexpr int KB = 24;          // partial sums of a row fetched per lane in one
 constexpr int ROW_WARPS = THREADS / 32 - 1;        // warps that sweep rows; the last warp handles row j+1
 constexpr int ROWS_PER_CTA = ROW_WARPS * (32 / TPR);
 constexpr int L2_BLOCK_ROWS = 0;  // plain (L2-allocating) loads below this many block rows: measured no gain on B200, off
-constexpr int DOT_CHUNK = 512;  // rows per panel dot-product unit (about the cost of one strip)
+constexpr int DOT_CHUNK = 32 * SW;  // rows per panel dot-product unit (about the cost of one strip)
 
 struct Params {
   double* A;
@@ -129,35 +132,60 @@ __device__ __forceinline__ void cta_reduce2(double& a, double& b, double* s_tmp 
   }
 }
 
-// Transposing butterfly: every lane holds 16 partial column sums; on return every lane holds the
-// complete sum of ONE column, index = bit4*8 + bit3*4 + bit2*2 + bit1 of the lane id.
-__device__ __forceinline__ double butterfly16(double (&p)[16], int lane) {
-  double q8[8], q4[4], q2[2];
+// Transposing butterfly: every lane holds SW partial column sums; on return every lane holds the
+// complete sum of ONE column: SW = 16: index = bit4*8 + bit3*4 + bit2*2 + bit1 of the lane id (lane pairs
+// agree); SW = 8: index = bit4*4 + bit3*2 + bit2 (groups of four lanes agree).
+__device__ __forceinline__ double butterfly(double (&p)[SW], int lane) {
   const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+  double q4[4], q2[2], q1;
+  if constexpr (SW == 16) {
+    double q8[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const double send = b4 ? p[k] : p[k + 8];
-    const double keep = b4 ? p[k + 8] : p[k];
-    q8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
+    for (int k = 0; k < 8; ++k) {
+      const double send = b4 ? p[k] : p[k + 8];
+      const double keep = b4 ? p[k + 8] : p[k];
+      q8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const double send = b3 ? q8[k] : q8[k + 4];
-    const double keep = b3 ? q8[k + 4] : q8[k];
-    q4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
+    for (int k = 0; k < 4; ++k) {
+      const double send = b3 ? q8[k] : q8[k + 4];
+      const double keep = b3 ? q8[k + 4] : q8[k];
+      q4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const double send = b2 ? q4[k] : q4[k + 2];
-    const double keep = b2 ? q4[k + 2] : q4[k];
-    q2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    for (int k = 0; k < 2; ++k) {
+      const double send = b2 ? q4[k] : q4[k + 2];
+      const double keep = b2 ? q4[k + 2] : q4[k];
+      q2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const double send = b1 ? q2[0] : q2[1];
+    const double keep = b1 ? q2[1] : q2[0];
+    q1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  } else {
+    static_assert(SW == 8 || SW == 16, "strip width");
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double send = b4 ? p[k] : p[k + 4];
+      const double keep = b4 ? p[k + 4] : p[k];
+      q4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double send = b3 ? q4[k] : q4[k + 2];
+      const double keep = b3 ? q4[k + 2] : q4[k];
+      q2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const double send = b2 ? q2[0] : q2[1];
+    const double keep = b2 ? q2[1] : q2[0];
+    q1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
   }
-  const double send = b1 ? q2[0] : q2[1];
-  const double keep = b1 ? q2[1] : q2[0];
-  double r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  r += __shfl_xor_sync(0xffffffffu, r, 1);
-  return r;
+  q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+  return q1;
 }
+// lanes that publish a column sum, and the column (inside the strip) they hold
+__device__ __forceinline__ bool col_writer(int lane) { return SW == 16 ? !(lane & 1) : !(lane & 3); }
+__device__ __forceinline__ int col_of_lane(int lane) { return SW == 16 ? ((lane >> 1) & 15) : ((lane >> 2) & 7); }
 
 // Work units of the product phase, in this order: the strips of block row b = 0, 1, ... (block row b
 // has SPT (b + 1) strips, the first at unit SPT b (b + 1) / 2), then the panel dot-product chunks.
@@ -336,7 +364,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
             vi1 = (ok1 && r1i > j) ? (r1i == j + 1 ? 1.0 : ab[r1i] * scale) : 0.0;
             newrow = false;
           }
-          double vcol;  // v at column cbase + (lane & 15)
+          double vcol;  // v at column cbase + (lane mod SW)
           {
             const int c = cbase + (lane & (SW - 1));
             vcol = (c < n && c > j) ? (c == j + 1 ? 1.0 : ab[c] * scale) : 0.0;
@@ -368,9 +396,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
               p[c] = y0 * vi0 + y1 * vi1;
             }
           }
-          const double cs = butterfly16(p, lane);
-          if (!(lane & 1)) {
-            const int cl = (lane >> 1) & 15;
+          const double cs = butterfly(p, lane);
+          if (col_writer(lane)) {
+            const int cl = col_of_lane(lane);
             const int cg = cbase + cl;
             if (cg < n) P.colpart[(size_t)I * n + cg] = cs;
             yv += cs * s_vj[warp][cl];

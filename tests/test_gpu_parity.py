@@ -561,6 +561,14 @@ def test_computeM_with_native_eigensolver():
         "rel = np.linalg.norm(got['Z'] - ref['Z']) / np.linalg.norm(ref['Z'])\n"
         "assert 'eig_sytrd' in rep and rep['eig_sytrd']['calls'] > 0, rep\n"
         "assert got['iters'] == ref['iters'] and rel < 1e-6, (got['iters'], ref['iters'], rel)\n"
+        "import ctypes as C\n"
+        "from rsoptsc_b200 import _lib\n"
+        "rng = np.random.default_rng(7); n = 1700\n"
+        "B = rng.standard_normal((n, n)); G = np.asfortranarray(B @ B.T / n)\n"
+        "lam = np.zeros(n); V = np.zeros((n, n), order='F'); dp = C.POINTER(C.c_double)\n"
+        "_lib.check(_lib.load().rsoptsc_debug_sym_eig(G.ctypes.data_as(dp), n, 1, lam.ctypes.data_as(dp), "
+        "V.ctypes.data_as(dp), 1, None))\n"
+        "assert np.abs(G @ V - V * lam).max() < 1e-12 * lam.max() and np.abs(V.T @ V - np.eye(n)).max() < 1e-11\n"
         "print('native eig path ok', rel)\n" % (root, os.path.join(root, "tests")))
     # ... and the own blocked back-transformation instead of cusolverDnDormtr (the default below 32,768 rows)
     env = dict(os.environ, RSOPTSC_EIG="native", RSOPTSC_BACKTRANSFORM="native")
