@@ -37,13 +37,13 @@ __global__ void k_build_U(const double* __restrict__ S, const double* __restrict
 
 }  // namespace
 
-void apply_q_left(const double* d_A, int64_t lda, const double* d_tau, int64_t n, double* d_Z) {
+void apply_q_left(const double* d_A, int64_t lda, const double* d_tau, int64_t n, double* d_Z, int64_t ncols) {
   Context& c = ctx();
-  if (n < 2) return;
+  if (n < 2 || ncols < 1) return;
   const int64_t nref = n - 1;                              // reflectors 0 .. n-2
   const int64_t nb = n >= 6000 ? 1024 : (n >= 1536 ? 512 : 128);
   const int64_t nblk = (nref + nb - 1) / nb;
-  DevBuf<double> Vb((size_t)n * nb), S((size_t)nb * nb), U((size_t)nb * nb), X((size_t)nb * n);
+  DevBuf<double> Vb((size_t)n * nb), S((size_t)nb * nb), U((size_t)nb * nb), X((size_t)nb * ncols);
   for (int64_t k = nblk - 1; k >= 0; --k) {
     const int64_t j0 = k * nb, nbk = std::min(nb, nref - j0), r0 = j0 + 1, m = n - r0;
     dim3 ge((unsigned)std::min<int64_t>(cdiv(m, 256), 256), (unsigned)nbk);
@@ -52,11 +52,11 @@ void apply_q_left(const double* d_A, int64_t lda, const double* d_tau, int64_t n
     dim3 gu((unsigned)cdiv(nbk, 128), (unsigned)nbk);
     RS_LAUNCH(k_build_U, gu, 128, 0, S.p, d_tau + j0, (int)nbk, U.p);
     double* Zr = d_Z + r0;
-    gemm_tn_ld(Vb.p, m, Zr, n, X.p, nbk, nbk, n, m);  // X = V^T Z            (nbk x n)
+    gemm_tn_ld(Vb.p, m, Zr, n, X.p, nbk, nbk, ncols, m);  // X = V^T Z            (nbk x ncols)
     const double mone = -1.0;
-    RS_CUBLAS(cublasDtrsm(c.cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)nbk, (int)n,
+    RS_CUBLAS(cublasDtrsm(c.cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)nbk, (int)ncols,
                           &mone, U.p, (int)nbk, X.p, (int)nbk));  // X <- -T X
-    gemm_nn_ld_acc(Vb.p, m, X.p, nbk, Zr, n, m, n, nbk);  // Z += V (-T V^T Z)
+    gemm_nn_ld_acc(Vb.p, m, X.p, nbk, Zr, n, m, ncols, nbk);  // Z += V (-T V^T Z)
   }
 }
 

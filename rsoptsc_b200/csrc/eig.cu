@@ -132,7 +132,7 @@ static int64_t native_min_n() {
   return t;
 }
 
-static void sym_eig_native(double* d_A, int64_t n, double* d_lam) {
+static void sym_eig_native(double* d_A, int64_t n, double* d_lam, double keep_above = -1.0e300) {
   Context& c = ctx();
   DevBuf<double> d(n), e(n), tau(n), Z((size_t)n * n);
   {
@@ -158,7 +158,17 @@ static void sym_eig_native(double* d_A, int64_t n, double* d_lam) {
     DevBuf<double> S1((size_t)n * n), S2((size_t)n * n);
     stedc_device(d.p, e.p, n, d_lam, Z.p, S1.p, S2.p);
   }
-  {
+  // eigenvalues ascending: the wanted eigenvectors are the trailing columns c0 .. n-1
+  int64_t c0 = 0;
+  if (keep_above > -1.0e299) {
+    std::vector<double> lam(n);
+    RS_CUDA(cudaMemcpyAsync(lam.data(), d_lam, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+    RS_CUDA(cudaStreamSynchronize(c.stream));
+    while (c0 < n && lam[c0] < keep_above) ++c0;
+  }
+  const int64_t ncols = n - c0;
+  double* Zk = Z.p + (size_t)c0 * n;
+  if (ncols > 0) {
     Phase ph("eig_backtransform");
     // cusolverDnDormtr (38 ms at 7,954 rows) is still ahead of the own blocked back-transformation (49 ms: its
     // panel-shaped GEMMs run at ~33 TF/s-eq) but overflows its 32-bit workspace above 32,768 rows.
@@ -170,20 +180,20 @@ static void sym_eig_native(double* d_A, int64_t n, double* d_lam) {
     }
     if (use_lib && n <= 32768) {
       int lwork = 0;
-      RS_CUSOLVER(cusolverDnDormtr_bufferSize(c.cusolver, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)n, (int)n,
-                                              d_A, (int)n, tau.p, Z.p, (int)n, &lwork));
+      RS_CUSOLVER(cusolverDnDormtr_bufferSize(c.cusolver, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)n, (int)ncols,
+                                              d_A, (int)n, tau.p, Zk, (int)n, &lwork));
       DevBuf<double> work((size_t)std::max(lwork, 1));
       DevBuf<int> info(1);
-      RS_CUSOLVER(cusolverDnDormtr(c.cusolver, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)n, (int)n, d_A,
-                                   (int)n, tau.p, Z.p, (int)n, work.p, lwork, info.p));
+      RS_CUSOLVER(cusolverDnDormtr(c.cusolver, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)n, (int)ncols, d_A,
+                                   (int)n, tau.p, Zk, (int)n, work.p, lwork, info.p));
       int hinfo = 0;
       RS_CUDA(cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
       RS_CUDA(cudaStreamSynchronize(c.stream));
       RS_REQUIRE(hinfo == 0, "back-transformation failed (info=" + std::to_string(hinfo) + ")");
     } else {
-      apply_q_left(d_A, n, tau.p, n, Z.p);
+      apply_q_left(d_A, n, tau.p, n, Zk, ncols);
     }
-    RS_CUDA(cudaMemcpyAsync(d_A, Z.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, c.stream));
+    RS_CUDA(cudaMemcpyAsync(d_A + (size_t)c0 * n, Zk, sizeof(double) * (size_t)n * ncols, cudaMemcpyDeviceToDevice, c.stream));
     RS_CUDA(cudaStreamSynchronize(c.stream));
   }
 }
@@ -197,9 +207,9 @@ void sym_eig_select(double* d_A, int64_t n, double* d_lam, int solver) {
 
 // A (n x n, lower triangle referenced) -> eigenvectors in A (when `vectors`), eigenvalues ascending
 // in d_lam.  Throws when the solver reports failure.
-void sym_eig(double* d_A, int64_t n, double* d_lam, bool vectors) {
+void sym_eig(double* d_A, int64_t n, double* d_lam, bool vectors, double keep_above) {
   RS_REQUIRE(n >= 1, "sym_eig: empty matrix");
-  if (vectors && native_min_n() >= 0 && n >= native_min_n() && n <= 65535) return sym_eig_native(d_A, n, d_lam);
+  if (vectors && native_min_n() >= 0 && n >= native_min_n() && n <= 65535) return sym_eig_native(d_A, n, d_lam, keep_above);
   sym_eig_library(d_A, n, d_lam, vectors);
 }
 

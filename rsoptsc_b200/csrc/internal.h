@@ -89,11 +89,13 @@ void tridiag_eig(std::vector<double>& d, std::vector<double>& e, std::vector<dou
 // ---- singular value thresholding (svt.cu) -------------------------------------------
 // eig.cu: dense symmetric eigensolver (lower triangle of A; eigenvectors overwrite A when requested,
 // eigenvalues ascending in d_lam)
-void sym_eig(double* d_A, int64_t n, double* d_lam, bool vectors);
+// keep_above: only the eigenvectors of eigenvalues >= keep_above are needed (the trailing columns, eigenvalues being
+// ascending); the other columns of A may be left undefined.  Default: all of them.
+void sym_eig(double* d_A, int64_t n, double* d_lam, bool vectors, double keep_above = -1.0e300);
 // same with eigenvectors, solver forced: 0 library (cuSOLVER), 1 native (sytrd_kernel.cuh + stedc.cu)
 void sym_eig_select(double* d_A, int64_t n, double* d_lam, int solver);
 // backtransform.cu: Z (n x n) <- Q Z, Q = product of the Householder reflectors stored by the tridiagonalisation
-void apply_q_left(const double* d_A, int64_t lda, const double* d_tau, int64_t n, double* d_Z);
+void apply_q_left(const double* d_A, int64_t lda, const double* d_tau, int64_t n, double* d_Z, int64_t ncols);  // Z: n x ncols, ld n
 
 struct SvtWorkspace {
   int64_t n = 0;

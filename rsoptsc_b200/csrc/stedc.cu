@@ -251,10 +251,13 @@ void stedc_device(const double* d_d, const double* d_e, int64_t n64, double* d_l
   DevBuf<int> dv_loff(L + 1), dv_zrow(n), dv_org(n);
   dv_d.upload(d.data(), n, c.stream);
   dv_loff.upload(loff.data(), L + 1, c.stream);
-  RS_LAUNCH(k_leaf_eig, (unsigned)L, LEAF, 0, dv_d.p, d_e, dv_loff.p, Qc, ldq, dv_lam.p);
   std::vector<double> lam(n);
-  dv_lam.download(lam.data(), n, c.stream);
-  RS_CUDA(cudaStreamSynchronize(c.stream));
+  {
+    Phase ph("stedc_leaves");
+    RS_LAUNCH(k_leaf_eig, (unsigned)L, LEAF, 0, dv_d.p, d_e, dv_loff.p, Qc, ldq, dv_lam.p);
+    dv_lam.download(lam.data(), n, c.stream);
+    RS_CUDA(cudaStreamSynchronize(c.stream));
+  }
 
   std::vector<Block> blocks;
   for (int b = 0; b < L; ++b) blocks.push_back({loff[b], loff[b + 1] - loff[b]});
@@ -265,6 +268,7 @@ void stedc_device(const double* d_d, const double* d_e, int64_t n64, double* d_l
   while (blocks.size() > 1) {
     const size_t nmerge = blocks.size() / 2;
     // ---- coupling vectors z = [last row of Q1 ; sign(beta) first row of Q2] --------------------
+    Phase* ph_plan = new Phase("stedc_plan_secular");
     std::fill(zsgn.begin(), zsgn.end(), 0.0);
     std::fill(zrow.begin(), zrow.end(), 0);
     for (size_t m = 0; m < nmerge; ++m) {
@@ -308,6 +312,7 @@ void stedc_device(const double* d_d, const double* d_e, int64_t n64, double* d_l
     dv_lamnew.download(lamnew.data(), n, c.stream);
     RS_CUDA(cudaStreamSynchronize(c.stream));
 
+    delete ph_plan;
     // ---- output order; stage 2 upload: positions -----------------------------------------------
     std::vector<char> pack2;
     std::vector<std::vector<int>> pos_nd(nmerge), pos_def(nmerge);
@@ -323,6 +328,7 @@ void stedc_device(const double* d_d, const double* d_e, int64_t n64, double* d_l
     if (!pack2.empty()) RS_CUDA(cudaMemcpyAsync(dv_pack2.p, pack2.data(), pack2.size(), cudaMemcpyHostToDevice, c.stream));
 
     // ---- per merge: M, then Q_next[block] = Q_cur[block] M -----------------------------------------
+    Phase ph_apply("stedc_apply");
     for (size_t m = 0; m < nmerge; ++m) {
       const MergePlan& P = plans[m];
       const int off = blocks[2 * m].off, nm = P.nm, k = P.k, nd = (int)P.idx_def.size(), nrot = (int)P.rots.size();

@@ -33,7 +33,8 @@ int64_t svt_inplace(SvtWorkspace& ws, double* d_A, int64_t n, double tau) {
   }
   {  // G -> V (columns), lam ascending
     Phase ph("eig");
-    sym_eig(ws.G.p, n, ws.lam.p, /*vectors=*/true);
+    // only the eigenvectors with sqrt(lambda) > tau enter J (margin: the count below is re-derived from lambda)
+    sym_eig(ws.G.p, n, ws.lam.p, /*vectors=*/true, tau * tau * (1.0 - 1e-9));
   }
   std::vector<double> lam(n);
   RS_CUDA(cudaMemcpyAsync(lam.data(), ws.lam.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));

@@ -198,6 +198,54 @@ struct UnitMap {
   __device__ __forceinline__ long long owner(long long u) const { return u * nw / total; }
 };
 
+// Between the end of a product phase and the next one (row phase + two grid synchronisations, ~7 us) the
+// memory system idles.  Every warp uses that window to pull the first PF_STRIPS strips of its NEXT run into
+// L2 (prefetch only: no registers held, and a line that the trailing update rewrites stays coherent).
+#ifndef RS_SYTRD_PF_STRIPS
+#define RS_SYTRD_PF_STRIPS 0  // measured on B200: 3 strips 234 ms, 6 strips 241 ms, none 227 ms at 7,954 rows -> off
+#endif
+constexpr int PF_STRIPS = RS_SYTRD_PF_STRIPS;
+__device__ __forceinline__ void prefetch_next_run(const Params& P, int jnext, int jjnext, long long gwarp, long long nwarps,
+                                                  int lane) {
+  if (PF_STRIPS == 0 || jnext + 1 >= P.n) return;
+  const int n = P.n;
+  const int Bmin = (jnext + 1) / TILE, mt = P.mB - Bmin;
+  const int nch = (n - jnext - 1 + DOT_CHUNK - 1) / DOT_CHUNK;
+  UnitMap um;
+  um.strips = um.first_of_row(mt);
+  um.total = um.strips + 2LL * jjnext * nch;
+  um.nw = nwarps < um.total ? nwarps : um.total;
+  if (gwarp >= um.nw) return;
+  long long u = um.start(gwarp);
+  long long uend = um.start(gwarp + 1);
+  if (uend > um.strips) uend = um.strips;
+  if (uend > u + PF_STRIPS) uend = u + PF_STRIPS;
+  if (u >= uend) return;
+  int b = (int)floor((sqrt(1.0 + 8.0 * (double)u / SPT) - 1.0) * 0.5);
+  if (b < 0) b = 0;
+  while (b > 0 && um.first_of_row(b) > u) --b;
+  while (um.first_of_row(b + 1) <= u) ++b;
+  int k = (int)(u - um.first_of_row(b));
+  const int half = lane & 1;
+  for (; u < uend; ++u) {
+    const int I = Bmin + b, J = Bmin + k / SPT, pass = k % SPT;
+    const int row0 = I * TILE + half * 32;
+#pragma unroll
+    for (int cc = 0; cc < SW; cc += 16) {
+      const int c = J * TILE + pass * SW + cc + (lane >> 1);
+      if ((lane >> 1) < SW - cc && c < n && row0 < n) {
+        const char* p = reinterpret_cast<const char*>(P.A + (long long)c * P.lda + row0);  // 256 bytes per half column
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
+        if (half) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 255));
+      }
+    }
+    if (++k == SPT * (b + 1)) { ++b; k = 0; }
+  }
+}
+
+__device__ __forceinline__ bool more_cols(int jj, int pw) { return jj + 1 < pw; }
+
 // Row i of the row phase, stage 1: V(i, t), W(i, t) for t = sub + u TPR < jj into vv / ww, and this
 // lane's share of y(i) (the row and column partial sums of the product phase).  No dependence on the
 // panel dot products, so these loads overlap their reduction.
@@ -433,6 +481,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
         if (lane == 0) P.pvec[(size_t)ch * (2 * NB) + q] = acc;
       }
     }
+    prefetch_next_run(P, j + 1, more_cols(jj, P.pw) ? jj + 1 : 0, gwarp, nwarps, lane);
     RS_PROF(2)
     if (P.prof != nullptr && tid == 0) { P.prof[16 + blockIdx.x] += clock64() - t3; }
     {
