@@ -78,9 +78,11 @@ __device__ __forceinline__ double warp_sum_fixed(double v) {
 
 // Grid-wide barrier + sum of two doubles per CTA.  Valid inputs in thread 0 of each CTA; every thread
 // of every CTA returns the same two sums (fixed summation order).  All global writes made by any CTA
-// before the call are visible to every CTA after it (release on the arrival counter, acquire on the
-// generation flag; bar.sync extends both to the whole CTA).  All CTAs are co-resident (cooperative
-// launch); the arrival counter is monotonic within a launch.
+// before the call are visible to every CTA after it (release reduction on the arrival counter, acquire
+// loads of the same counter; bar.sync extends both to the whole CTA).  All CTAs are co-resident
+// (cooperative launch); the arrival counter is monotonic within a launch.  The per-CTA partials are
+// double-buffered by generation parity: a CTA can only write generation g+2 after every CTA has
+// arrived at g+1, i.e. after every CTA has finished reading generation g.
 __device__ __forceinline__ void grid_allreduce2(unsigned long long* slots, unsigned nblocks, unsigned& gen, double& v0,
                                                 double& v1, double* s_out) {
   const unsigned tid = threadIdx.x;
