@@ -230,6 +230,8 @@ void stedc_device(const double* d_d, const double* d_e, int64_t n64, double* d_l
   if (n > 1) RS_CUDA(cudaMemcpyAsync(e.data(), d_e, sizeof(double) * (n - 1), cudaMemcpyDeviceToHost, c.stream));
   RS_CUDA(cudaStreamSynchronize(c.stream));
 
+  for (int i = 0; i < n; ++i)
+    RS_REQUIRE(std::isfinite(d[i]) && (i + 1 >= n || std::isfinite(e[i])), "symmetric eigensolver: non-finite entries in the matrix");
   std::vector<int> loff;
   stedc::make_leaves(n, LEAF, loff);
   const int L = (int)loff.size() - 1;
