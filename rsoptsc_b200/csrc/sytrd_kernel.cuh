@@ -105,9 +105,17 @@ __device__ __forceinline__ void grid_allreduce2(unsigned long long* slots, unsig
   __syncthreads();
   if (tid < 32) {
     double a = 0, b = 0;
-    for (unsigned k = tid; k < nblocks; k += 32) {
-      a += part[2 * k];
-      b += part[2 * k + 1];
+    // all partials of a lane are requested in one batch (one L2 round trip), then added in a fixed order
+    const double2* part2 = reinterpret_cast<const double2*>(part);
+    for (unsigned k0 = tid; k0 < nblocks; k0 += 32 * 8) {
+      double2 t[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const unsigned k = k0 + 32u * q;
+        t[q] = (k < nblocks) ? part2[k] : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { a += t[q].x; b += t[q].y; }
     }
     a = warp_sum_fixed(a);
     b = warp_sum_fixed(b);
@@ -616,6 +624,7 @@ inline cudaError_t run(cublasHandle_t blas, cudaStream_t stream, double* A, int6
   P.colpart = w;  w += (size_t)mB * n;
   P.abuf = w;     w += 2 * n;
   P.pvec = w;     w += 2 * NB * (n / DOT_CHUNK + 1);
+  if ((w - work) & 1) ++w;  // 16-byte alignment for the double2 loads of the partials
   P.slots = reinterpret_cast<unsigned long long*>(w);
   P.prof = prof;
   cublasSetStream(blas, stream);
