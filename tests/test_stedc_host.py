@@ -108,3 +108,40 @@ def test_glued_clusters(lib):
     d = np.tile(blk_d, 30)
     e = np.concatenate([np.concatenate([blk_e, [1e-8]]) for _ in range(30)])[:-1]
     check(lib, d, e, 8)
+
+
+def _tridiag_with_spectrum(lam, rng):
+    """Tridiagonal matrix (via a random orthogonal similarity + Hessenberg reduction) with the given spectrum."""
+    from scipy.linalg import hessenberg
+    n = len(lam)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    H = hessenberg((Q * lam) @ Q.T)
+    return np.diag(H).copy(), np.diag(H, -1).copy()
+
+
+@pytest.mark.parametrize("kind", ["repeated", "geometric", "two_clusters", "tiny_plus_huge"])
+def test_prescribed_spectra(lib, kind):
+    rng = np.random.default_rng(11)
+    n = 180
+    if kind == "repeated":          # exactly repeated eigenvalues: deflation by Givens rotations
+        lam = np.repeat(np.arange(1.0, 10.0), n // 9)
+    elif kind == "geometric":       # 16 orders of magnitude
+        lam = 10.0 ** np.linspace(-14, 2, n)
+    elif kind == "two_clusters":    # two tight clusters, relative width 1e-13
+        lam = np.concatenate([1.0 + 1e-13 * rng.standard_normal(n // 2), 3.0 + 1e-13 * rng.standard_normal(n // 2)])
+    else:                           # the SVT's shape: many values at rounding level next to O(1) ones
+        lam = np.concatenate([1e-17 * rng.random(n - 20), 1.0 + rng.random(20)])
+    lam = np.sort(lam)
+    d, e = _tridiag_with_spectrum(lam, rng)
+    T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    got, Q, stats = run(lib, d, e, 16)
+    scale = np.abs(lam).max()
+    assert np.abs(got - np.linalg.eigvalsh(T)).max() <= 5e-14 * n * scale
+    assert np.abs(Q.T @ Q - np.eye(n)).max() <= 5e-14 * n
+    assert np.abs(T @ Q - Q * got).max() <= 5e-14 * n * scale
+
+
+def test_larger_random(lib):
+    rng = np.random.default_rng(12)
+    n = 700
+    check(lib, rng.standard_normal(n), rng.standard_normal(n - 1), 32)
