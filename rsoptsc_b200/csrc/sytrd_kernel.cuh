@@ -49,7 +49,6 @@ constexpr int RPT = NB / TPR;   // panel columns per thread in the row-wise phas
 constexpr int KB = 24;          // partial sums of a row fetched per lane in one batch
 constexpr int ROW_WARPS = THREADS / 32 - 1;        // warps that sweep rows; the last warp handles row j+1
 constexpr int ROWS_PER_CTA = ROW_WARPS * (32 / TPR);
-constexpr int L2_BLOCK_ROWS = 0;  // plain (L2-allocating) loads below this many block rows: measured no gain on B200, off
 constexpr int DOT_CHUNK = 32 * SW;  // rows per panel dot-product unit (about the cost of one strip)
 
 struct Params {
@@ -83,8 +82,14 @@ __device__ __forceinline__ double warp_sum_fixed(double v) {
 // (cooperative launch); the arrival counter is monotonic within a launch.  The per-CTA partials are
 // double-buffered by generation parity: a CTA can only write generation g+2 after every CTA has
 // arrived at g+1, i.e. after every CTA has finished reading generation g.
+struct NoWork {
+  __device__ void operator()() const {}
+};
+// `while_waiting` is run by warps 1.. of every CTA while thread 0 waits for the other CTAs: free issue slots
+// for work that does not depend on the barrier (staging of the next product phase).
+template <class F = NoWork>
 __device__ __forceinline__ void grid_allreduce2(unsigned long long* slots, unsigned nblocks, unsigned& gen, double& v0,
-                                                double& v1, double* s_out) {
+                                                double& v1, double* s_out, F while_waiting = F()) {
   const unsigned tid = threadIdx.x;
   ++gen;
   double* part = reinterpret_cast<double*>(slots) + (size_t)(gen & 1u) * MAX_GRID * 2;  // double-buffered partials
@@ -102,6 +107,7 @@ __device__ __forceinline__ void grid_allreduce2(unsigned long long* slots, unsig
       if (++spins > (1u << 25)) __trap();  // never hang the device
     } while (seen < target);
   }
+  if (tid >= 32) while_waiting();
   __syncthreads();
   if (tid < 32) {
     double a = 0, b = 0;
@@ -208,16 +214,19 @@ struct UnitMap {
   __device__ __forceinline__ long long owner(long long u) const { return u * nw / total; }
 };
 
-// Between the end of a product phase and the next one (row phase + two grid synchronisations, ~7 us) the
-// memory system idles.  Every warp uses that window to pull the first PF_STRIPS strips of its NEXT run into
-// L2 (prefetch only: no registers held, and a line that the trailing update rewrites stays coherent).
-#ifndef RS_SYTRD_PF_STRIPS
-#define RS_SYTRD_PF_STRIPS 0  // measured on B200: 3 strips 234 ms, 6 strips 241 ms, none 227 ms at 7,954 rows -> off
+// Between the end of a product phase and the next one (row phase + two grid synchronisations, ~10 us) the
+// memory system idles.  Every warp uses that window to stage the FIRST strip of its next run in shared
+// memory with cp.async (8 KB per warp, 128 KB per SM, ~19 MB over the grid: a fifth of an average column).
+// The strip's unit id is returned (-1: nothing staged); the product phase compares it with the unit it is
+// about to process, so a mismatch only costs the staging.  (An L2-only prefetch of the same strips was
+// measured slower on B200.)
+#ifndef RS_SYTRD_STAGE
+#define RS_SYTRD_STAGE 1
 #endif
-constexpr int PF_STRIPS = RS_SYTRD_PF_STRIPS;
-__device__ __forceinline__ void prefetch_next_run(const Params& P, int jnext, int jjnext, long long gwarp, long long nwarps,
-                                                  int lane) {
-  if (PF_STRIPS == 0 || jnext + 1 >= P.n) return;
+constexpr int STAGE_DOUBLES = TILE * SW;  // per warp
+__device__ __forceinline__ long long stage_next_strip(const Params& P, int jnext, int jjnext, long long gwarp, long long nwarps,
+                                                      int lane, double* sbuf) {
+  if (!RS_SYTRD_STAGE || jnext + 1 >= P.n) return -1;
   const int n = P.n;
   const int Bmin = (jnext + 1) / TILE, mt = P.mB - Bmin;
   const int nch = (n - jnext - 1 + DOT_CHUNK - 1) / DOT_CHUNK;
@@ -225,33 +234,28 @@ __device__ __forceinline__ void prefetch_next_run(const Params& P, int jnext, in
   um.strips = um.first_of_row(mt);
   um.total = um.strips + 2LL * jjnext * nch;
   um.nw = nwarps < um.total ? nwarps : um.total;
-  if (gwarp >= um.nw) return;
-  long long u = um.start(gwarp);
-  long long uend = um.start(gwarp + 1);
-  if (uend > um.strips) uend = um.strips;
-  if (uend > u + PF_STRIPS) uend = u + PF_STRIPS;
-  if (u >= uend) return;
+  if (gwarp >= um.nw) return -1;
+  const long long u = um.start(gwarp);
+  if (u >= um.strips || u >= um.start(gwarp + 1)) return -1;
   int b = (int)floor((sqrt(1.0 + 8.0 * (double)u / SPT) - 1.0) * 0.5);
   if (b < 0) b = 0;
   while (b > 0 && um.first_of_row(b) > u) --b;
   while (um.first_of_row(b + 1) <= u) ++b;
-  int k = (int)(u - um.first_of_row(b));
-  const int half = lane & 1;
-  for (; u < uend; ++u) {
-    const int I = Bmin + b, J = Bmin + k / SPT, pass = k % SPT;
-    const int row0 = I * TILE + half * 32;
+  const int k = (int)(u - um.first_of_row(b));
+  const int I = Bmin + b, J = Bmin + k / SPT, pass = k % SPT;
+  const int cbase = J * TILE + pass * SW;
+  const int r0 = I * TILE + lane, r1 = r0 + 32;
+  const unsigned s0 = (unsigned)__cvta_generic_to_shared(sbuf + lane), s1 = (unsigned)__cvta_generic_to_shared(sbuf + lane + 32);
 #pragma unroll
-    for (int cc = 0; cc < SW; cc += 16) {
-      const int c = J * TILE + pass * SW + cc + (lane >> 1);
-      if ((lane >> 1) < SW - cc && c < n && row0 < n) {
-        const char* p = reinterpret_cast<const char*>(P.A + (long long)c * P.lda + row0);  // 256 bytes per half column
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
-        if (half) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 255));
-      }
+  for (int c = 0; c < SW; ++c) {
+    if (cbase + c < n) {
+      const double* col = P.A + (long long)(cbase + c) * P.lda;
+      if (r0 < n) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s0 + 8u * TILE * c), "l"(col + r0) : "memory");
+      if (r1 < n) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s1 + 8u * TILE * c), "l"(col + r1) : "memory");
     }
-    if (++k == SPT * (b + 1)) { ++b; k = 0; }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  return u;
 }
 
 __device__ __forceinline__ bool more_cols(int jj, int pw) { return jj + 1 < pw; }
@@ -310,6 +314,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
   __shared__ double s_p1[NB], s_p2[NB];      // W^T v, V^T v
   __shared__ double s_vr[NB], s_wr[NB];      // row j+1 of V and W
   __shared__ double s_vj[THREADS / 32][SW];  // per-warp copy of v over the strip's columns
+  extern __shared__ double s_stage[];         // THREADS/32 x STAGE_DOUBLES: staged first strips
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned nblocks = gridDim.x;
@@ -328,6 +333,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
   const bool row_warp = warp < ROW_WARPS;
   const int gwarp = blockIdx.x * (THREADS / 32) + warp;
   const long long nwarps = (long long)nblocks * (THREADS / 32);
+
+  double* sbuf = s_stage + (size_t)warp * STAGE_DOUBLES;
+  long long staged = -1;  // unit whose matrix entries sit in sbuf
 
   const bool prof = P.prof != nullptr && blockIdx.x == 0 && tid == 0;
   long long tc = prof ? clock64() : 0;
@@ -353,7 +361,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
     double* abn = P.abuf + (size_t)((j + 1) & 1) * n;     // next column
 
     cta_reduce2(ss, alpha_part, s_tmp);
-    grid_allreduce2(P.slots, nblocks, gen, ss, alpha_part, s_out);  // #1: ||x||^2 and alpha
+    // #1: ||x||^2 and alpha.  The row phase is over, DRAM idles until the product phase: the waiting warps stage
+    // their first strip of it (column j, whose unit map does not depend on the reflector).
+    {
+      auto stage = [&]() {
+        staged = stage_next_strip(P, j, jj, gwarp, nwarps, lane, sbuf);
+      };
+      grid_allreduce2(P.slots, nblocks, gen, ss, alpha_part, s_out, stage);
+    }
     RS_PROF(1)
 
     // ---------------- reflector (every thread, identical arithmetic) ----------------------------
@@ -381,7 +396,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
     um.total = um.strips + 2LL * jj * nch;
     um.nw = nwarps < um.total ? nwarps : um.total;
     double yv = 0;  // this lane's share of v^T A22 v
-    const bool stream_loads = mt > L2_BLOCK_ROWS;
     if (gwarp < um.nw) {
       long long u = um.start(gwarp);
       const long long uend = um.start(gwarp + 1);
@@ -403,18 +417,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
           // matrix loads first (the long latency), then the pieces of v
           double a0[SW], a1[SW], p[SW];
           const double* Ab = A + (long long)cbase * lda;
+          if (staged == u) {
+            // this strip was staged in shared memory while the grid was synchronising
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
 #pragma unroll
-          for (int c = 0; c < SW; ++c) {
-            const bool okc = cbase + c < n;
-            const double* col = Ab + (long long)c * lda;
-            // streaming loads (do not evict the panel from L2) while the triangle exceeds L2; plain
-            // loads once it fits, so that the tail of the factorisation runs out of L2
-            if (stream_loads) {
+            for (int c = 0; c < SW; ++c) {
+              const bool okc = cbase + c < n;
+              a0[c] = (ok0 && okc) ? sbuf[c * TILE + lane] : 0.0;
+              a1[c] = (ok1 && okc) ? sbuf[c * TILE + lane + 32] : 0.0;
+            }
+            __syncwarp();
+            staged = -1;
+            if (prof) P.prof[12] += 1;
+          } else {
+#pragma unroll
+            for (int c = 0; c < SW; ++c) {
+              const bool okc = cbase + c < n;
+              const double* col = Ab + (long long)c * lda;
+              // streaming loads: do not evict the panel and the partial sums from L2
               a0[c] = (ok0 && okc) ? __ldcs(col + r0i) : 0.0;
               a1[c] = (ok1 && okc) ? __ldcs(col + r1i) : 0.0;
-            } else {
-              a0[c] = (ok0 && okc) ? col[r0i] : 0.0;
-              a1[c] = (ok1 && okc) ? col[r1i] : 0.0;
             }
           }
           if (newrow) {
@@ -491,7 +514,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
         if (lane == 0) P.pvec[(size_t)ch * (2 * NB) + q] = acc;
       }
     }
-    prefetch_next_run(P, j + 1, more_cols(jj, P.pw) ? jj + 1 : 0, gwarp, nwarps, lane);
+    if (staged >= 0) {  // a staged strip that was not consumed (cannot happen with identical unit maps)
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      staged = -1;
+    }
     RS_PROF(2)
     if (P.prof != nullptr && tid == 0) { P.prof[16 + blockIdx.x] += clock64() - t3; }
     {
@@ -592,6 +618,7 @@ __global__ void k_restore_subdiag(double* A, long long lda, int n, const double*
   if (i == n - 1) d[n - 1] = A[(long long)(n - 1) * lda + (n - 1)];
 }
 
+constexpr size_t STAGE_BYTES = (size_t)(THREADS / 32) * STAGE_DOUBLES * sizeof(double);
 inline size_t rowpart_doubles(int64_t n) {
   const int64_t mB = (n + TILE - 1) / TILE;
   return (size_t)(MAX_GRID * (THREADS / 32) + mB + 1) * TILE;
@@ -628,6 +655,12 @@ inline cudaError_t run(cublasHandle_t blas, cudaStream_t stream, double* A, int6
   P.slots = reinterpret_cast<unsigned long long*>(w);
   P.prof = prof;
   cublasSetStream(blas, stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t st = cudaFuncSetAttribute(k_latrd_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGE_BYTES);
+    if (st != cudaSuccess) return st;
+    attr_set = true;
+  }
   for (int64_t j0 = 0; j0 < n - 1; j0 += NB) {
     const int pw = (int)((n - 1 - j0) < NB ? (n - 1 - j0) : NB);
     P.j0 = (int)j0; P.pw = pw;
@@ -640,7 +673,7 @@ inline cudaError_t run(cublasHandle_t blas, cudaStream_t stream, double* A, int6
       for (int jj = 0; jj < pw; ++jj) { const double m = (double)(n - (j0 + jj) - 1); bytes += 4.0 * m * m; }
       hooks->before(hooks->user, bytes);
     }
-    st = cudaLaunchCooperativeKernel((void*)k_latrd_panel, dim3(grid), dim3(THREADS), args, 0, stream);
+    st = cudaLaunchCooperativeKernel((void*)k_latrd_panel, dim3(grid), dim3(THREADS), args, STAGE_BYTES, stream);
     if (hooks && hooks->after) hooks->after(hooks->user);
     if (st != cudaSuccess) return st;
     if (launches) ++*launches;

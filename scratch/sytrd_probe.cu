@@ -110,7 +110,9 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(h, prof, 8 * 1100, cudaMemcpyDeviceToHost));
     const char* names[7] = {"(unused)", "allreduce1 (norm, alpha)", "reflector + product phase", "allreduce2 (v^T A v)",
                             "row phase c (row loop)", "row phase a (panel dots)", "row phase b (w(j+1), alpha2)"};
-    for (int k = 0; k < 7; ++k)
+    printf("  staged strips consumed by warp 0 of CTA 0: %lld of %lld columns\n", h[12], (long long)n);
+
+    for (int k = 0; k < 6; ++k)
       printf("  prof %-28s %8.2f ms total over %d reps (cycles/1.9GHz)  %.2f us/column\n", names[k], h[k] / 1.9e6, reps,
              h[k] / 1.9e3 / reps / (double)n);
   }
