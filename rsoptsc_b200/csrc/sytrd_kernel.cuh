@@ -21,6 +21,8 @@
 //    run, column sums go through a transposing shuffle butterfly;
 //  * every partial sum has its own slot in a scratch array that is reduced in a fixed order, so
 //    results are bit-reproducible;
+//  * while a CTA waits in the all-reduce that precedes the product phase (DRAM idle), its warps
+//    stage the first strip of their run in shared memory with cp.async;
 //  * the rank-2NB trailing update between panels is one cublasDsyr2k.
 //
 // HBM traffic: sum_j 4 (n-j)^2 = (4/3) n^3 bytes for the products (the floor of any one-stage
