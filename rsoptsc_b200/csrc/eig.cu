@@ -1,11 +1,14 @@
 // Dense symmetric eigensolver used by the SVT (a4), the PCA spectrum (a2) and the Laplacian
-// spectrum (a14).  This is the one library call that dominates the path; it
-// is isolated here so that a native two-stage solver can replace it.
-//   n <= 32,768 : cusolverDnXsyevd (64-bit API; the legacy entry point overflows its int workspace
-//                 size above ~23,000 rows)
-//   n  > 32,768 : cusolverDnXsyevd rejects the size (probed in scratch/eig_limit_probe.cu), so the
-//                 block goes through cusolverMgSyevd on this process's device (probed in
-//                 scratch/mg_probe.cu: 33,000 rows in 36.8 s on one B200)
+// spectrum (a14) -- the dominant cost of the path.
+//   4,000 <= n <= 65,535, eigenvectors wanted : native solver -- cooperative-kernel tridiagonalisation
+//                 (sytrd_kernel.cuh), tridiagonal divide and conquer (stedc.cu), back-transformation
+//                 (cusolverDnDormtr up to 32,768 rows, backtransform.cu above)
+//   otherwise, n <= 32,768 : cusolverDnXsyevd (64-bit API; the legacy entry point overflows its int
+//                 workspace size above ~23,000 rows)
+//   n  > 32,768 : cusolverDnXsyevd rejects the size (probed in scratch/eig_limit_probe.cu);
+//                 cusolverMgSyevd on this process's device (scratch/mg_probe.cu: 33,000 rows in 36.8 s
+//                 on one B200; the native solver needs 14.9 s) -- only for RSOPTSC_EIG=cusolver,
+//                 value-only spectra and blocks above 65,535 rows
 #include <cusolverMg.h>
 #include <dlfcn.h>
 
