@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RSOPTSC_ABI_VERSION 1
+#define RSOPTSC_ABI_VERSION 2
 
 /* stop codes of the ADMM (R/SimilarityM.R:134-137, :157-162, :191-194) */
 #define RSOPTSC_STOP_MAXITER 1
@@ -56,6 +56,24 @@ double rsoptsc_counter(const char* name);
 const char* rsoptsc_phase_name(int32_t i);
 int rsoptsc_timer_begin(const char* name);
 int rsoptsc_timer_end(const char* name);
+
+/* ---- multi-GPU: one process per GPU, one communicator per process ------
+ * After rsoptsc_comm_init with nranks > 1 the library is SPMD: every rank calls the same entry point
+ * with the same inputs (the genes x cells matrix is replicated, <= 2.4 GB) and receives the same
+ * outputs.  Inside, one computeM problem is split: column blocks of Z/E/Y1/XXZ/Y3/J per rank
+ * (R/SimilarityM.R:164-187 is column-local), the SVT Gram / eigensolver / reconstruction of the large
+ * connected blocks split across all ranks with NCCL all-gathers of column panels and a fused
+ * peer-memory tridiagonalisation, the stop-rule norms by NCCL allreduce of the genes x genes Gram.
+ * The reference has no counterpart (single R process); R hosts bind it through one R worker per GPU. */
+/* 128-byte NCCL unique id, created on rank 0 and handed to every rank by the host's own channel. */
+int rsoptsc_comm_unique_id(uint8_t* id128);
+/* Collective over the nranks processes; call after rsoptsc_init(device).  nranks == 1 is a no-op. */
+int rsoptsc_comm_init(int32_t nranks, int32_t rank, const uint8_t* id128);
+int rsoptsc_comm_finalize(void);
+/* nranks / rank of the active communicator (1 / 0 without one); p2p = 1 once the peer-mapped exchange
+ * regions of the fused tridiagonalisation exist; collectives / bytes: data-path NCCL calls issued and
+ * their payload since rsoptsc_comm_init.  Any pointer may be NULL. */
+int rsoptsc_comm_info(int32_t* nranks, int32_t* rank, int32_t* p2p, int64_t* collectives, double* bytes);
 
 /* device-memory helpers for the *_dev entry points */
 int rsoptsc_dev_alloc(void** dptr, int64_t bytes);
@@ -197,7 +215,8 @@ int rsoptsc_debug_gemm(int32_t op, const double* A, const double* B, double* C, 
 /* Symmetric eigen-decomposition of a host matrix (n x n column-major, lower triangle referenced) with
  * one of the two solvers behind the SVT of rsoptsc_computeM (R/SimilarityM.R:142-155):
  *   solver 0: cuSOLVER syevd;  solver 1: native (cooperative-kernel tridiagonalisation, tridiagonal
- *   divide and conquer with tcgen05 GEMMs, library back-transformation).
+ *   divide and conquer with tcgen05 GEMMs, back-transformation);  solver 2: the native solver as a
+ *   collective over the ranks of the active communicator (every rank passes the same matrix).
  * lam_out (n) ascending eigenvalues, V_out (n x n, may be NULL) eigenvectors.  reps >= 1 repetitions
  * are timed with CUDA events; *ms_out (may be NULL) = mean ms per call. */
 int rsoptsc_debug_sym_eig(const double* A, int64_t n, int32_t solver, double* lam_out, double* V_out,
@@ -210,6 +229,13 @@ int rsoptsc_debug_sym_eig(const double* A, int64_t n, int32_t solver, double* la
 int rsoptsc_host_tridiag_eig(int32_t k, double* d, const double* e, double* V);
 /* The K rule of R/SimilarityM.R:61-72 applied to a descending PCA spectrum of length len. */
 int32_t rsoptsc_host_choose_K(const double* eig, int64_t len);
+/* Multi-GPU split of one computeM problem over nranks ranks (no GPU needed): for the neighbour table
+ * idx (n x K row-major, as rsoptsc_computeM) owner[j] = rank that holds the column-local state of
+ * cell j; component[j] = connected component of the support graph (numbered by lowest cell);
+ * split[j] = 1 when that component has >= split_min cells and is cut across all ranks.  Any output
+ * may be NULL. */
+int rsoptsc_host_shard_owner(const int32_t* idx, int64_t n, int32_t K, int32_t nranks, int64_t split_min,
+                             int32_t* owner, int32_t* component, int32_t* split);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,10 @@ SIGNATURES = {
     "rsoptsc_counter": (C.c_double, [C.c_char_p]),
     "rsoptsc_timer_begin": (C.c_int, [C.c_char_p]),
     "rsoptsc_timer_end": (C.c_int, [C.c_char_p]),
+    "rsoptsc_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "rsoptsc_comm_init": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]),
+    "rsoptsc_comm_finalize": (C.c_int, []),
+    "rsoptsc_comm_info": (C.c_int, [c_int32_p, c_int32_p, c_int32_p, c_int64_p, c_double_p]),
     "rsoptsc_dev_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "rsoptsc_dev_free": (C.c_int, [C.c_void_p]),
     "rsoptsc_dev_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
@@ -76,6 +80,8 @@ SIGNATURES = {
     "rsoptsc_debug_sym_eig": (C.c_int, [c_double_p, C.c_int64, C.c_int32, c_double_p, c_double_p, C.c_int32, c_double_p]),
     "rsoptsc_host_tridiag_eig": (C.c_int, [C.c_int32, c_double_p, c_double_p, c_double_p]),
     "rsoptsc_host_choose_K": (C.c_int32, [c_double_p, C.c_int64]),
+    "rsoptsc_host_shard_owner": (C.c_int, [c_int32_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, c_int32_p, c_int32_p,
+                                           c_int32_p]),
 }
 
 

@@ -16,7 +16,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
          "--expt-relaxed-constexpr", "-I", os.path.join(HERE, "..", "include")]
-LIBS = ["-lcublas", "-lcusolver", "-lcudart", "-ldl"]  # libcusolverMg is dlopen'ed on demand (eig.cu)
+LIBS = ["-lcublas", "-lcusolver", "-lcudart", "-lnccl", "-ldl"]  # libcusolverMg is dlopen'ed on demand (eig.cu)
 
 
 def sources():

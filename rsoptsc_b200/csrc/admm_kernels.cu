@@ -36,7 +36,8 @@ __global__ void k_E_update(const double* __restrict__ XXZ, const double* __restr
 
 void admm_E_update(AdmmState& st, double lambda, double mu) {
   Phase ph("E_update");
-  RS_LAUNCH(k_E_update, (unsigned)st.n, CT, 0, st.XXZ.p, st.Y1.p, st.m, lambda, mu, st.E.p, st.R.p);
+  if (st.nloc > 0)
+    RS_LAUNCH(k_E_update, (unsigned)st.nloc, CT, 0, st.XXZ.p, st.Y1.p, st.m, lambda, mu, st.E.p, st.R.p);
 }
 
 // ---- a7 + a8: gradient step on the support, Y2 update --------------------------------
@@ -45,16 +46,16 @@ void admm_E_update(AdmmState& st, double lambda, double mu) {
 __global__ void k_Z_update(const double* __restrict__ X, const double* __restrict__ R, int64_t m,
                            const int* __restrict__ colptr, const int* __restrict__ rowidx,
                            const int* __restrict__ csrpos, const double* __restrict__ q, double mu, double eta,
-                           double* __restrict__ Zs, double* __restrict__ Y2) {
+                           double* __restrict__ Zs, double* __restrict__ Y2, const int* __restrict__ cols) {
   __shared__ double sm[CT / 32 + 1];
-  const int j = blockIdx.x;
+  const int j = cols ? cols[blockIdx.x] : blockIdx.x;  // cell; the m x nloc arrays are indexed by blockIdx.x
   const int q0 = colptr[j], q1 = colptr[j + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double part = 0;
   for (int e = q0 + threadIdx.x; e < q1; e += CT) part += Zs[csrpos[e]];
   const double colsum_old = block_sum<CT>(part, sm);
   const double rj = 1.0 - colsum_old + Y2[j] / mu;
-  const double* Rj = R + (int64_t)j * m;
+  const double* Rj = R + (int64_t)blockIdx.x * m;
   double newpart = 0;
   for (int e = q0 + warp; e < q1; e += CT / 32) {
     const double* Xi = X + (int64_t)rowidx[e] * m;
@@ -75,8 +76,9 @@ __global__ void k_Z_update(const double* __restrict__ X, const double* __restric
 
 void admm_Z_update(AdmmState& st, const Support& s, double mu, double eta) {
   Phase ph("Z_update");
-  RS_LAUNCH(k_Z_update, (unsigned)st.n, CT, 0, st.X, st.R.p, st.m, s.colptr.p, s.rowidx.p, s.csrpos.p, st.q.p, mu,
-            eta, st.Zs.p, st.Y2.p);
+  if (st.nloc > 0)
+    RS_LAUNCH(k_Z_update, (unsigned)st.nloc, CT, 0, st.X, st.R.p, st.m, s.colptr.p, s.rowidx.p, s.csrpos.p, st.q.p, mu,
+              eta, st.Zs.p, st.Y2.p, st.cols);
 }
 
 // ---- a9 + a10: XXZ = X - X Z ; Y1 += mu (XXZ - E) ; M = XXZ - E -----------------------
@@ -84,13 +86,13 @@ __global__ void k_residual(const double* __restrict__ X, int64_t m, const int* _
                            const int* __restrict__ rowidx, const int* __restrict__ csrpos,
                            const double* __restrict__ Zs, const double* __restrict__ E, double mu, int update_duals,
                            double* __restrict__ XXZ, double* __restrict__ Y1, double* __restrict__ M,
-                           double* __restrict__ colacc) {
+                           double* __restrict__ colacc, const int* __restrict__ cols) {
   __shared__ double sm[CT / 32 + 1];
   __shared__ int s_row[CT];
   __shared__ double s_z[CT];
-  const int j = blockIdx.x;
+  const int j = cols ? cols[blockIdx.x] : blockIdx.x;
   const int q0 = colptr[j], q1 = colptr[j + 1];
-  const int64_t base = (int64_t)j * m;
+  const int64_t base = (int64_t)blockIdx.x * m, xbase = (int64_t)j * m;
   double nrm = 0;
   for (int64_t t0 = 0; t0 < m; t0 += CT) {
     const int64_t t = t0 + threadIdx.x;
@@ -107,7 +109,7 @@ __global__ void k_residual(const double* __restrict__ X, int64_t m, const int* _
         for (int c = 0; c < cnt; ++c) acc += s_z[c] * X[(int64_t)s_row[c] * m + t];
     }
     if (t < m) {
-      const double r = X[base + t] - acc;
+      const double r = X[xbase + t] - acc;
       XXZ[base + t] = r;
       const double d = r - E[base + t];
       if (update_duals) {
@@ -118,7 +120,7 @@ __global__ void k_residual(const double* __restrict__ X, int64_t m, const int* _
     }
   }
   nrm = block_sum<CT>(nrm, sm);
-  if (threadIdx.x == 0) colacc[j] = nrm;
+  if (threadIdx.x == 0) colacc[blockIdx.x] = nrm;
 }
 
 __global__ void k_sum_vec(const double* __restrict__ v, int64_t n, double* __restrict__ out) {
@@ -131,11 +133,12 @@ __global__ void k_sum_vec(const double* __restrict__ v, int64_t n, double* __res
 
 double admm_residual_update(AdmmState& st, const Support& s, double mu, bool update_duals) {
   Phase ph("residual");
-  RS_LAUNCH(k_residual, (unsigned)st.n, CT, 0, st.X, st.m, s.colptr.p, s.rowidx.p, s.csrpos.p, st.Zs.p, st.E.p, mu,
-            update_duals ? 1 : 0, st.XXZ.p, st.Y1.p, st.M.p, st.colacc.p);
-  RS_LAUNCH(k_sum_vec, 1, CT, 0, st.colacc.p, st.n, st.colacc.p + st.n);
+  if (st.nloc == 0) return 0.0;
+  RS_LAUNCH(k_residual, (unsigned)st.nloc, CT, 0, st.X, st.m, s.colptr.p, s.rowidx.p, s.csrpos.p, st.Zs.p, st.E.p, mu,
+            update_duals ? 1 : 0, st.XXZ.p, st.Y1.p, st.M.p, st.colacc.p, st.cols);
+  RS_LAUNCH(k_sum_vec, 1, CT, 0, st.colacc.p, st.nloc, st.colacc.p + st.nloc);
   double h = 0;
-  RS_CUDA(cudaMemcpyAsync(&h, st.colacc.p + st.n, sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+  RS_CUDA(cudaMemcpyAsync(&h, st.colacc.p + st.nloc, sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
   RS_CUDA(cudaStreamSynchronize(ctx().stream));
   return h;
 }

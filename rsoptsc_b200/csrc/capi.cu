@@ -4,6 +4,7 @@
 #include <unordered_map>
 
 #include "../../include/rsoptsc_b200.h"
+#include "comm.h"
 #include "gemm.h"
 #include "internal.h"
 
@@ -178,6 +179,7 @@ int rsoptsc_init(int device) { return guarded([&] { ensure_init(device); }); }
 int rsoptsc_finalize(void) {
   return guarded([&] {
     if (!g_ctx.initialized) return;
+    comm_finalize();
     resolve_phases();
     release_dense_scratch();
     pool_trim();
@@ -231,6 +233,26 @@ int64_t rsoptsc_phase_calls(const char* name) {
   for (size_t i = 0; i < g_phase_names.size(); ++i)
     if (g_phase_names[i] == name) return g_phases[i].calls;
   return -1;
+}
+
+int rsoptsc_comm_unique_id(uint8_t* id128) {
+  return guarded([&] {
+    RS_REQUIRE(id128 != nullptr, "comm_unique_id: null buffer");
+    comm_unique_id(id128);
+  });
+}
+int rsoptsc_comm_init(int32_t nranks, int32_t rank, const uint8_t* id128) {
+  return guarded([&] { comm_init(nranks, rank, id128); });
+}
+int rsoptsc_comm_finalize(void) { return guarded([&] { comm_finalize(); }); }
+int rsoptsc_comm_info(int32_t* nranks, int32_t* rank, int32_t* p2p, int64_t* collectives, double* bytes) {
+  const Comm& cm = comm();
+  if (nranks) *nranks = cm.nranks;
+  if (rank) *rank = cm.rank;
+  if (p2p) *p2p = cm.p2p ? 1 : 0;
+  if (collectives) *collectives = cm.collectives;
+  if (bytes) *bytes = cm.collective_bytes;
+  return 0;
 }
 
 int rsoptsc_dev_alloc(void** dptr, int64_t bytes) {
@@ -707,7 +729,7 @@ int rsoptsc_debug_sym_eig(const double* A, int64_t n, int32_t solver, double* la
                           double* ms_out) {
   return guarded([&] {
     cudaStream_t s = ctx().stream;
-    RS_REQUIRE(A && lam_out && n >= 1 && n <= 65535 && reps >= 1 && (solver == 0 || solver == 1), "debug_sym_eig: bad arguments");
+    RS_REQUIRE(A && lam_out && n >= 1 && n <= 65535 && reps >= 1 && solver >= 0 && solver <= 2, "debug_sym_eig: bad arguments");
     const size_t nn = (size_t)n * n;
     DevBuf<double> a0(nn), a(nn), lam(n);
     a0.upload(A, nn, s);
@@ -717,7 +739,8 @@ int rsoptsc_debug_sym_eig(const double* A, int64_t n, int32_t solver, double* la
     for (int r = 0; r <= reps; ++r) {  // r == 0 is the warm-up
       RS_CUDA(cudaMemcpyAsync(a.p, a0.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, s));
       RS_CUDA(cudaEventRecord(e0, s));
-      sym_eig_select(a.p, n, lam.p, solver);
+      if (solver == 2) sym_eig(a.p, n, lam.p, true, -1.0e300, /*collective=*/true);  // all ranks of the communicator
+      else sym_eig_select(a.p, n, lam.p, solver);
       RS_CUDA(cudaEventRecord(e1, s));
       RS_CUDA(cudaEventSynchronize(e1));
       float ms = 0;
@@ -739,6 +762,25 @@ int rsoptsc_host_tridiag_eig(int32_t k, double* d, const double* e, double* V) {
     tridiag_eig(dd, ee, V ? &vv : nullptr);
     std::memcpy(d, dd.data(), sizeof(double) * k);
     if (V) std::memcpy(V, vv.data(), sizeof(double) * (size_t)k * k);
+  });
+}
+int rsoptsc_host_shard_owner(const int32_t* idx, int64_t n, int32_t K, int32_t nranks, int64_t split_min,
+                             int32_t* owner, int32_t* component, int32_t* split) {
+  return guarded([&] {
+    RS_REQUIRE(idx && n > 0 && K > 0 && nranks >= 1 && nranks <= MAX_RANKS, "host_shard_owner: bad arguments");
+    Support sup;
+    build_support_from_idx(sup, idx, n, K, /*device=*/false);
+    for (int r = 0; r < nranks; ++r) {
+      ShardPlan plan;
+      build_shard_plan(sup, nranks, r, split_min, plan, /*device=*/false);
+      if (owner)
+        for (int j : plan.own_cols) owner[j] = r;
+      if (r == 0)
+        for (int64_t j = 0; j < n; ++j) {
+          if (component) component[j] = sup.h_comp[j];
+          if (split) split[j] = plan.big[sup.h_comp[j]] ? 1 : 0;
+        }
+    }
   });
 }
 int32_t rsoptsc_host_choose_K(const double* eig, int64_t len) {

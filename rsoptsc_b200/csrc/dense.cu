@@ -4,6 +4,7 @@
 //   a11 threshold + symmetrise          R/SimilarityM.R:94-95
 // All matrices are column-major FP64.  Reductions are two-stage with a fixed order so that
 // results are run-to-run deterministic.
+#include "comm.h"
 #include "internal.h"
 
 namespace rs {
@@ -124,13 +125,19 @@ void normalize_columns(const double* d_data, int64_t m, int64_t n, double* d_X) 
 }
 
 // ---- A = Z - Y3/mu -------------------------------------------------------------------
+// (y3 and a start at the same offset of two 256-byte aligned allocations: one scalar head element
+// restores the 16-byte alignment of the double2 body when that offset is odd)
 __global__ void k_scale_neg(const double* __restrict__ y3, double mu, int64_t count, double* __restrict__ a) {
+  const int64_t head = (reinterpret_cast<uintptr_t>(y3) & 8) ? 1 : 0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 2;
-  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i + 1 < count; i += stride) {
+  for (int64_t i = head + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i + 1 < count; i += stride) {
     const double2 v = *reinterpret_cast<const double2*>(y3 + i);
     *reinterpret_cast<double2*>(a + i) = make_double2(-(v.x / mu), -(v.y / mu));
   }
-  if ((count & 1) && blockIdx.x == 0 && threadIdx.x == 0) a[count - 1] = -(y3[count - 1] / mu);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (head && count > 0) a[0] = -(y3[0] / mu);
+    if (((count - head) & 1) && count > head) a[count - 1] = -(y3[count - 1] / mu);
+  }
 }
 __global__ void k_scatter_add(const int* __restrict__ rowof, const int* __restrict__ col, const double* __restrict__ zs,
                               int64_t nnz, int64_t n, double scale, double* __restrict__ a) {
@@ -138,22 +145,39 @@ __global__ void k_scatter_add(const int* __restrict__ rowof, const int* __restri
   if (p < nnz) a[(int64_t)rowof[p] + (int64_t)col[p] * n] += scale * zs[p];
 }
 
-// entry p of the support lives at block-storage offset off[p] (Support::dense_off)
-__global__ void k_scatter_add_off(const long long* __restrict__ off, const double* __restrict__ zs, int64_t nnz,
-                                  double scale, double* __restrict__ a) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < nnz) a[off[p]] += scale * zs[p];
+// entry p of the support lives at block-storage offset off[p] (Support::dense_off); `sel` (may be null)
+// restricts the pass to a list of entries (the columns a rank owns)
+__global__ void k_scatter_add_off(const long long* __restrict__ off, const double* __restrict__ zs, int64_t cnt,
+                                  double scale, double* __restrict__ a, const int* __restrict__ sel = nullptr) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cnt) return;
+  const int64_t p = sel ? sel[t] : t;
+  a[off[p]] += scale * zs[p];
 }
 
 // A = Z - Y3/mu on the block-diagonal storage; fro2[c] = ||A_c||_F^2 per connected component
 void build_A(const Support& s, const double* d_Zs, const double* d_Y3, double mu, double* d_A,
-             std::vector<double>& fro2) {
+             std::vector<double>& fro2, const ShardPlan* plan) {
   Phase ph("build_A");
   const int64_t nn = s.total_dense;
-  RS_LAUNCH(k_scale_neg, RED_BLOCKS * 2, 256, 0, d_Y3, mu, nn, d_A);
-  if (s.nnz) RS_LAUNCH(k_scatter_add_off, cdiv(s.nnz, 256), 256, 0, s.dense_off.p, d_Zs, s.nnz, 1.0, d_A);
-  fro2.resize(s.comp_n.size());
+  if (plan && plan->on) {
+    // owned columns only; the blocks that are split across the ranks are then gathered (their SVT is collective)
+    for (const auto& sg : plan->segs) {
+      const int blocks = (int)std::min<int64_t>(RED_BLOCKS * 2, std::max<int64_t>(1, sg.count / 2048));
+      RS_LAUNCH(k_scale_neg, blocks, 256, 0, d_Y3 + sg.off, mu, sg.count, d_A + sg.off);
+    }
+    if (plan->nent())
+      RS_LAUNCH(k_scatter_add_off, cdiv(plan->nent(), 256), 256, 0, s.dense_off.p, d_Zs, plan->nent(), 1.0, d_A,
+                plan->d_own_entries.p);
+    for (size_t c = 0; c < s.comp_n.size(); ++c)
+      if (plan->big[c]) comm_allgather_cols(d_A + s.comp_off[c], s.comp_n[c], plan->cb[c]);
+  } else {
+    RS_LAUNCH(k_scale_neg, RED_BLOCKS * 2, 256, 0, d_Y3, mu, nn, d_A);
+    if (s.nnz) RS_LAUNCH(k_scatter_add_off, cdiv(s.nnz, 256), 256, 0, s.dense_off.p, d_Zs, s.nnz, 1.0, d_A);
+  }
+  fro2.assign(s.comp_n.size(), 0.0);
   for (size_t c = 0; c < s.comp_n.size(); ++c) {
+    if (plan && plan->on && !plan->big[c] && plan->owner[c] != plan->rank) continue;
     const int64_t cnt = s.comp_n[c] * s.comp_n[c];
     const int blocks = (int)std::min<int64_t>(RED_BLOCKS, std::max<int64_t>(1, cnt / 4096));
     RS_LAUNCH(k_frob2, blocks, RED_THREADS, 0, d_A + s.comp_off[c], cnt, red().partial.p);
@@ -163,19 +187,23 @@ void build_A(const Support& s, const double* d_Zs, const double* d_Y3, double mu
 
 // ---- q[p] = Zs - J + Y3/mu on the support -------------------------------------------
 __global__ void k_gather_term(const long long* __restrict__ doff, const double* __restrict__ zs,
-                              const double* __restrict__ J, const double* __restrict__ y3, double mu, int64_t nnz,
-                              double* __restrict__ q) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= nnz) return;
+                              const double* __restrict__ J, const double* __restrict__ y3, double mu, int64_t cnt,
+                              double* __restrict__ q, const int* __restrict__ sel) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cnt) return;
+  const int64_t p = sel ? sel[t] : t;
   const int64_t off = doff[p];
   const double j = J ? J[off] : 0.0;
   q[p] = zs[p] - j + y3[off] / mu;
 }
 void gather_support_term(const Support& s, const double* d_Zs, const double* d_J, const double* d_Y3, double mu,
-                         double* d_q) {
+                         double* d_q, const ShardPlan* plan) {
   Phase ph("gather");
-  if (s.nnz)
-    RS_LAUNCH(k_gather_term, cdiv(s.nnz, 256), 256, 0, s.dense_off.p, d_Zs, d_J, d_Y3, mu, s.nnz, d_q);
+  const bool sh = plan && plan->on;
+  const int64_t cnt = sh ? plan->nent() : s.nnz;
+  if (cnt)
+    RS_LAUNCH(k_gather_term, cdiv(cnt, 256), 256, 0, s.dense_off.p, d_Zs, d_J, d_Y3, mu, cnt, d_q,
+              sh ? plan->d_own_entries.p : (const int*)nullptr);
 }
 
 // ---- Y3 += mu (Z - J) ------------------------------------------------------------------
@@ -183,8 +211,9 @@ __global__ void k_y3_sub_J(const double* __restrict__ J, double mu, int64_t coun
                            double* __restrict__ partial) {
   __shared__ double sm[RED_THREADS / 32 + 1];
   double acc = 0;
+  const int64_t head = (reinterpret_cast<uintptr_t>(y3) & 8) ? 1 : 0;  // see k_scale_neg
   const int64_t stride = (int64_t)gridDim.x * RED_THREADS * 2;
-  for (int64_t i = ((int64_t)blockIdx.x * RED_THREADS + threadIdx.x) * 2; i + 1 < count; i += stride) {
+  for (int64_t i = head + ((int64_t)blockIdx.x * RED_THREADS + threadIdx.x) * 2; i + 1 < count; i += stride) {
     const double2 j = *reinterpret_cast<const double2*>(J + i);
     double2 y = *reinterpret_cast<double2*>(y3 + i);
     y.x -= mu * j.x;
@@ -192,22 +221,30 @@ __global__ void k_y3_sub_J(const double* __restrict__ J, double mu, int64_t coun
     *reinterpret_cast<double2*>(y3 + i) = y;
     acc += j.x * j.x + j.y * j.y;
   }
-  if ((count & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    const double j = J[count - 1];
-    y3[count - 1] -= mu * j;
-    acc += j * j;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (head && count > 0) {
+      const double j = J[0];
+      y3[0] -= mu * j;
+      acc += j * j;
+    }
+    if (((count - head) & 1) && count > head) {
+      const double j = J[count - 1];
+      y3[count - 1] -= mu * j;
+      acc += j * j;
+    }
   }
   acc = block_sum<RED_THREADS>(acc, sm);
   if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 // sparse part: Y3[i,j] += mu*Zs ; partial sums of (Zs-J)^2 - J^2 over the support
 __global__ void k_y3_add_Z(const long long* __restrict__ doff, const double* __restrict__ zs,
-                           const double* __restrict__ J, double mu, int64_t nnz, double* __restrict__ y3,
-                           double* __restrict__ partial) {
+                           const double* __restrict__ J, double mu, int64_t cnt, double* __restrict__ y3,
+                           double* __restrict__ partial, const int* __restrict__ sel) {
   __shared__ double sm[RED_THREADS / 32 + 1];
   double acc = 0;
   const int64_t stride = (int64_t)gridDim.x * RED_THREADS;
-  for (int64_t p = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x; p < nnz; p += stride) {
+  for (int64_t t = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x; t < cnt; t += stride) {
+    const int64_t p = sel ? sel[t] : t;
     const int64_t off = doff[p];
     const double z = zs[p];
     const double j = J ? J[off] : 0.0;
@@ -218,19 +255,30 @@ __global__ void k_y3_add_Z(const long long* __restrict__ doff, const double* __r
   if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
-double update_Y3(const Support& s, const double* d_Zs, const double* d_J, double mu, double* d_Y3) {
+// Returns this rank's share of ||Z - J||_F^2 (the caller sums over ranks; NaN propagates to its finiteness check).
+double update_Y3(const Support& s, const double* d_Zs, const double* d_J, double mu, double* d_Y3,
+                 const ShardPlan* plan) {
   Phase ph("update_Y3");
   const int64_t nn = s.total_dense;  // block-diagonal storage (sum n_c^2)
+  const bool sh = plan && plan->on;
   double total = 0;
   // order matters: the sparse kernel reads J on the support, so it may run after the dense one
-  if (d_J) {
+  if (d_J && !sh) {
     RS_LAUNCH(k_y3_sub_J, RED_BLOCKS, RED_THREADS, 0, d_J, mu, nn, d_Y3, red().partial.p);
     total += finish_sum(RED_BLOCKS);
+  } else if (d_J) {
+    for (const auto& sg : plan->segs) {
+      const int blocks = (int)std::min<int64_t>(RED_BLOCKS, std::max<int64_t>(1, sg.count / 4096));
+      RS_LAUNCH(k_y3_sub_J, blocks, RED_THREADS, 0, d_J + sg.off, mu, sg.count, d_Y3 + sg.off, red().partial.p);
+      total += finish_sum(blocks);
+    }
   }
   const int blocks = 148;
-  RS_LAUNCH(k_y3_add_Z, blocks, RED_THREADS, 0, s.dense_off.p, d_Zs, d_J, mu, s.nnz, d_Y3, red().partial.p);
+  const int64_t cnt = sh ? plan->nent() : s.nnz;
+  RS_LAUNCH(k_y3_add_Z, blocks, RED_THREADS, 0, s.dense_off.p, d_Zs, d_J, mu, cnt, d_Y3, red().partial.p,
+            sh ? plan->d_own_entries.p : (const int*)nullptr);
   total += finish_sum(blocks);
-  return total > 0 ? total : 0.0;
+  return total;
 }
 
 // ---- upper triangle <- lower triangle (column-major d x d) -----------------------------------
@@ -322,9 +370,28 @@ void threshold_symmetrise_sparse(const Support& s, const double* d_Zs, double* d
   RS_CUDA(cudaMemsetAsync(d_W, 0, sizeof(double) * s.n * s.n, ctx().stream));
   if (s.nnz) RS_LAUNCH(k_symmetrise_sparse, cdiv(s.nnz, 256), 256, 0, s.rowof.p, s.col.p, d_Zs, s.nnz, s.n, d_W);
 }
-void scatter_support_blocks(const Support& s, const double* d_Zs, double* d_Zb) {
+void scatter_support_blocks(const Support& s, const double* d_Zs, double* d_Zb, const ShardPlan* plan) {
   RS_CUDA(cudaMemsetAsync(d_Zb, 0, sizeof(double) * s.total_dense, ctx().stream));
-  if (s.nnz) RS_LAUNCH(k_scatter_add_off, cdiv(s.nnz, 256), 256, 0, s.dense_off.p, d_Zs, s.nnz, 1.0, d_Zb);
+  const bool sh = plan && plan->on;
+  const int64_t cnt = sh ? plan->nent() : s.nnz;
+  if (cnt)
+    RS_LAUNCH(k_scatter_add_off, cdiv(cnt, 256), 256, 0, s.dense_off.p, d_Zs, cnt, 1.0, d_Zb,
+              sh ? plan->d_own_entries.p : (const int*)nullptr);
+}
+// tmp[p] = Zs[p] for the owned entries, 0 elsewhere; summed over the ranks every entry has exactly one owner
+__global__ void k_copy_selected(const double* __restrict__ src, const int* __restrict__ sel, int64_t cnt,
+                                double* __restrict__ dst) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < cnt) dst[sel[t]] = src[sel[t]];
+}
+void assemble_support_values(const Support& s, const ShardPlan& plan, double* d_Zs) {
+  if (!plan.on || !s.nnz) return;
+  DevBuf<double> tmp((size_t)s.nnz);
+  tmp.zero(ctx().stream);
+  if (plan.nent()) RS_LAUNCH(k_copy_selected, cdiv(plan.nent(), 256), 256, 0, d_Zs, plan.d_own_entries.p, plan.nent(), tmp.p);
+  comm_allreduce_sum(tmp.p, (size_t)s.nnz);
+  RS_CUDA(cudaMemcpyAsync(d_Zs, tmp.p, sizeof(double) * s.nnz, cudaMemcpyDeviceToDevice, ctx().stream));
+  RS_CUDA(cudaStreamSynchronize(ctx().stream));
 }
 void scatter_support_dense(const Support& s, const double* d_Zs, double* d_Z) {
   Phase ph("symm");

@@ -12,6 +12,7 @@
 #include <cusolverMg.h>
 #include <dlfcn.h>
 
+#include "comm.h"
 #include "internal.h"
 #include "sytrd_kernel.cuh"
 
@@ -118,7 +119,11 @@ static void sym_eig_mg(double* d_A, int64_t n, double* d_lam, bool vectors) {
 
 // ---- native solver: own tridiagonalisation (sytrd_kernel.cuh) + own tridiagonal divide and conquer
 // (stedc.cu, GEMMs on tcgen05) + own blocked back-transformation (backtransform.cu, GEMMs on tcgen05) ---
-void stedc_device(const double* d_d, const double* d_e, int64_t n, double* d_lam, double* d_Z, double* d_S1, double* d_S2);
+void stedc_device(const double* d_d, const double* d_e, int64_t n, double* d_lam, double* d_Z, double* d_S1, double* d_S2,
+                  bool collective);
+// sytrd_mg.cu: the fused multi-GPU tridiagonalisation (all ranks, replicated matrix in, replicated reflectors out)
+bool sytrd_mg_available(int64_t n);
+void sytrd_mg_run(double* d_A, int64_t n, double* d_d, double* d_e, double* d_tau);
 
 // RSOPTSC_EIG=cusolver forces the library path, RSOPTSC_EIG=native lowers the size threshold to 256
 // (parity tests); default: native from RSOPTSC_NATIVE_MIN_N rows (4000: below that cuSOLVER's lower per-column latency
@@ -135,10 +140,14 @@ static int64_t native_min_n() {
   return t;
 }
 
-static void sym_eig_native(double* d_A, int64_t n, double* d_lam, double keep_above = -1.0e300) {
+static void sym_eig_native(double* d_A, int64_t n, double* d_lam, double keep_above = -1.0e300, bool collective = false) {
   Context& c = ctx();
+  collective = collective && sharded();
   DevBuf<double> d(n), e(n), tau(n), Z((size_t)n * n);
-  {
+  if (collective && sytrd_mg_available(n)) {
+    Phase ph("eig_sytrd");
+    sytrd_mg_run(d_A, n, d.p, e.p, tau.p);
+  } else {
     Phase ph("eig_sytrd");
     DevBuf<double> work(sytrd::workspace_doubles(n));
     int64_t launches = 0;
@@ -159,7 +168,7 @@ static void sym_eig_native(double* d_A, int64_t n, double* d_lam, double keep_ab
   {
     Phase ph("eig_stedc");
     DevBuf<double> S1((size_t)n * n), S2((size_t)n * n);
-    stedc_device(d.p, e.p, n, d_lam, Z.p, S1.p, S2.p);
+    stedc_device(d.p, e.p, n, d_lam, Z.p, S1.p, S2.p, collective);
   }
   // eigenvalues ascending: the wanted eigenvectors are the trailing columns c0 .. n-1
   int64_t c0 = 0;
@@ -171,7 +180,17 @@ static void sym_eig_native(double* d_A, int64_t n, double* d_lam, double keep_ab
   }
   const int64_t ncols = n - c0;
   double* Zk = Z.p + (size_t)c0 * n;
-  if (ncols > 0) {
+  if (ncols > 0 && collective) {
+    // every rank back-transforms one panel of the wanted eigenvectors (own blocked compact-WY routine, GEMMs on
+    // tcgen05), the panels are all-gathered
+    Phase ph("eig_backtransform");
+    const std::vector<int64_t> zb = split_even(ncols, comm().nranks, 128);
+    const int64_t z0 = zb[comm().rank], z1 = zb[comm().rank + 1];
+    if (z1 > z0) apply_q_left(d_A, n, tau.p, n, Zk + (size_t)z0 * n, z1 - z0);
+    comm_allgather_cols(Zk, n, zb);
+    RS_CUDA(cudaMemcpyAsync(d_A + (size_t)c0 * n, Zk, sizeof(double) * (size_t)n * ncols, cudaMemcpyDeviceToDevice, c.stream));
+    RS_CUDA(cudaStreamSynchronize(c.stream));
+  } else if (ncols > 0) {
     Phase ph("eig_backtransform");
     // cusolverDnDormtr (38 ms at 7,954 rows) is still ahead of the own blocked back-transformation (49 ms: its
     // panel-shaped GEMMs run at ~33 TF/s-eq) but overflows its 32-bit workspace above 32,768 rows.
@@ -210,9 +229,11 @@ void sym_eig_select(double* d_A, int64_t n, double* d_lam, int solver) {
 
 // A (n x n, lower triangle referenced) -> eigenvectors in A (when `vectors`), eigenvalues ascending
 // in d_lam.  Throws when the solver reports failure.
-void sym_eig(double* d_A, int64_t n, double* d_lam, bool vectors, double keep_above) {
+void sym_eig(double* d_A, int64_t n, double* d_lam, bool vectors, double keep_above, bool collective) {
   RS_REQUIRE(n >= 1, "sym_eig: empty matrix");
-  if (vectors && native_min_n() >= 0 && n >= native_min_n() && n <= 65535) return sym_eig_native(d_A, n, d_lam, keep_above);
+  // collective calls always take the native solver: its stages are the ones that are split across the ranks
+  if (vectors && n <= 65535 && ((collective && sharded() && n >= 2) || (native_min_n() >= 0 && n >= native_min_n())))
+    return sym_eig_native(d_A, n, d_lam, keep_above, collective);
   sym_eig_library(d_A, n, d_lam, vectors);
 }
 

@@ -19,6 +19,8 @@ void ozaki_gemm_nn_ld_acc(const double* A, int64_t lda, const double* B, int64_t
 void ozaki_gemm_tn_ld(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M,
                       int64_t N, int64_t K);
 void ozaki_gemm_tn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
+void ozaki_gemm_nt_ld(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M,
+                      int64_t N, int64_t K);
 
 static int g_backend = -1;  // 0 cublas, 1 ozaki
 int gemm_backend() {
@@ -92,6 +94,13 @@ void gemm_nt(const double* A, const double* B, double* C, int64_t M, int64_t N, 
   const double one = 1.0, zero = 0.0;
   RS_CUBLAS(cublasDgemm(ctx().cublas, CUBLAS_OP_N, CUBLAS_OP_T, (int)M, (int)N, (int)K, &one, A, (int)M, B, (int)N,
                         &zero, C, (int)M));
+}
+void gemm_nt_ld(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t N,
+                int64_t K) {
+  if (use_ozaki_panel(M, N, K)) return ozaki_gemm_nt_ld(A, lda, B, ldb, C, ldc, M, N, K);
+  const double one = 1.0, zero = 0.0;
+  RS_CUBLAS(cublasDgemm(ctx().cublas, CUBLAS_OP_N, CUBLAS_OP_T, (int)M, (int)N, (int)K, &one, A, (int)lda, B, (int)ldb,
+                        &zero, C, (int)ldc));
 }
 void gemm_tn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K) {
   if (use_ozaki(M, N, K)) return ozaki_gemm_tn(A, B, C, M, N, K);

@@ -23,6 +23,9 @@ void gemm_tn_ld(const double* A, int64_t lda, const double* B, int64_t ldb, doub
                 int64_t K);
 // C (M x N) = A (M x K) * B^T, B: N x K
 void gemm_nt(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
+// same with explicit leading dimensions
+void gemm_nt_ld(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M, int64_t N,
+                int64_t K);
 // C (M x N) = A^T * B, A: K x M, B: K x N
 void gemm_tn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
 }  // namespace rs

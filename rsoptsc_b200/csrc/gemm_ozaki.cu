@@ -524,6 +524,13 @@ void ozaki_gemm_nt(const double* A, const double* B, double* C, int64_t M, int64
   oz::slice_operand(B, N, N, K, /*contig=*/false, ozaki_slices(), b);
   oz::run(a, b, C, M, N, M, false, false);
 }
+void ozaki_gemm_nt_ld(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M,
+                      int64_t N, int64_t K) {
+  oz::Operand a, b;
+  oz::slice_operand(A, lda, M, K, /*contig=*/false, ozaki_slices(), a);
+  oz::slice_operand(B, ldb, N, K, /*contig=*/false, ozaki_slices(), b);
+  oz::run(a, b, C, M, N, ldc, false, false);
+}
 void ozaki_gemm_tn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K) {
   oz::Operand a, b;
   oz::slice_operand(A, K, M, K, /*contig=*/true, ozaki_slices(), a);

@@ -40,32 +40,62 @@ struct Support {
   std::vector<int64_t> comp_n, comp_off;  // block sizes / offsets (in doubles) into the dense state
   int64_t total_dense = 0;                // sum n_c^2
   DevBuf<long long> dense_off;            // per support entry: offset of (i,j) inside the block storage
+  std::vector<int> h_comp, h_local;       // per cell: its component and its index inside the component
 };
-void build_support_from_idx(Support& s, const int32_t* h_idx, int64_t n, int K);
+
+// Multi-GPU split of one computeM problem.  Cells (columns of Z, E, Y1, XXZ, Y3,
+// J -- column-local per R/SimilarityM.R:164-187) are owned by exactly one rank:
+//   * components with at least split_min cells ("big") are cut into one contiguous range of their
+//     local columns per rank; their SVT is collective (svt_sharded);
+//   * smaller components belong to one rank each (largest first onto the least loaded rank, cost
+//     n_c^3), together with all their column-local state; their SVT is local.
+struct ShardPlan {
+  bool on = false;
+  int P = 1, rank = 0;
+  std::vector<char> big;                  // per component
+  std::vector<int> owner;                 // per component: owning rank, -1 for big components
+  std::vector<std::vector<int64_t>> cb;   // big components: P + 1 local column boundaries
+  std::vector<int> own_cols;              // cells owned by this rank, ascending
+  std::vector<int> own_entries;           // CSR positions of the support entries in owned columns
+  DevBuf<int> d_own_cols, d_own_entries;
+  struct Seg { int64_t off, count; };
+  std::vector<Seg> segs;                  // owned parts of the block-diagonal dense storage
+  int64_t nloc() const { return (int64_t)own_cols.size(); }
+  int64_t nent() const { return (int64_t)own_entries.size(); }
+};
+void build_shard_plan(const Support& s, int P, int rank, int64_t split_min, ShardPlan& plan, bool device = true);
+int64_t shard_split_min();  // RSOPTSC_SPLIT_MIN_N, default 2048
+void build_support_from_idx(Support& s, const int32_t* h_idx, int64_t n, int K, bool device = true);
 void build_support_from_dense_mask(Support& s, const double* h_D, int64_t n);
 
 // ---- dense elementwise (dense.cu) ---------------------------------------------------
 void normalize_columns(const double* d_data, int64_t m, int64_t n, double* d_X);
 // A = -Y3/mu (+ Z scattered on the support) in block-diagonal storage; fro2[c] = ||A_c||_F^2
 void build_A(const Support& s, const double* d_Zs, const double* d_Y3, double mu, double* d_A,
-             std::vector<double>& fro2);
+             std::vector<double>& fro2, const ShardPlan* plan = nullptr);
 // q[p] = Zs[p] - J[i,j] + Y3[i,j]/mu on the support (J may be null == 0)
 void gather_support_term(const Support& s, const double* d_Zs, const double* d_J, const double* d_Y3,
-                         double mu, double* d_q);
+                         double mu, double* d_q, const ShardPlan* plan = nullptr);
 // Y3 += mu*(Z - J) ; returns ||Z - J||_F^2   (J may be null == 0)
-double update_Y3(const Support& s, const double* d_Zs, const double* d_J, double mu, double* d_Y3);
+double update_Y3(const Support& s, const double* d_Zs, const double* d_J, double mu, double* d_Y3,
+                 const ShardPlan* plan = nullptr);
+// sharded runs: Zs of the owned columns is current on every rank, the rest is stale -> make it whole again
+void assemble_support_values(const Support& s, const ShardPlan& plan, double* d_Zs);
 void scale_columns(double* d_T, int64_t rows, int64_t cols, const double* d_scale);
 void copy_scale_columns(const double* d_src, int64_t rows, int64_t cols, const double* d_scale, double* d_dst);
 void mirror_lower(double* d_B, int64_t d);  // upper triangle <- lower triangle
 void threshold_symmetrise_dense(const double* d_Z, int64_t n, double* d_W);
 void threshold_symmetrise_sparse(const Support& s, const double* d_Zs, double* d_W /* n x n, zeroed here */);
 void scatter_support_dense(const Support& s, const double* d_Zs, double* d_Z /* n x n, zeroed here */);
-void scatter_support_blocks(const Support& s, const double* d_Zs, double* d_Zb /* block storage, zeroed here */);
+void scatter_support_blocks(const Support& s, const double* d_Zs, double* d_Zb /* block storage, zeroed here */,
+                            const ShardPlan* plan = nullptr);
 double frob2(const double* d_a, int64_t count);
 
 // ---- column-local ADMM step (admm_kernels.cu) ---------------------------------------
 struct AdmmState {
   int64_t m = 0, n = 0;
+  int64_t nloc = 0;           // columns held by this rank (== n unless sharded)
+  const int* cols = nullptr;  // their global indices (device; null == identity)
   const double* X = nullptr;  // m x n normalised
   DevBuf<double> Zs;          // nnz, CSR order
   DevBuf<double> XXZ, E, Y1, R, M;  // m x n
@@ -82,6 +112,9 @@ double admm_residual_update(AdmmState& st, const Support& s, double mu, bool upd
 // Largest singular value of the column-major rows x cols matrix (Lanczos on the smaller Gram
 // operator, full reorthogonalisation).  rel_tol on the Ritz value.
 double spectral_norm(const double* d_M, int64_t rows, int64_t cols, double rel_tol = 2e-10);
+// same for a matrix whose COLUMNS are split across the ranks (d_M: rows x cols_local on this rank):
+// Gram of the row side summed over ranks (NCCL allreduce), identical result on every rank
+double spectral_norm_colsharded(const double* d_M, int64_t rows, int64_t cols_local, double rel_tol = 2e-10);
 // Host: eigen-decomposition of a symmetric tridiagonal (d: k diag, e: k-1 off-diag).
 // On return d holds ascending eigenvalues, Zv (k x k column-major, may be null) eigenvectors.
 void tridiag_eig(std::vector<double>& d, std::vector<double>& e, std::vector<double>* Zv, bool last_row_only = false);
@@ -91,7 +124,9 @@ void tridiag_eig(std::vector<double>& d, std::vector<double>& e, std::vector<dou
 // eigenvalues ascending in d_lam)
 // keep_above: only the eigenvectors of eigenvalues >= keep_above are needed (the trailing columns, eigenvalues being
 // ascending); the other columns of A may be left undefined.  Default: all of them.
-void sym_eig(double* d_A, int64_t n, double* d_lam, bool vectors, double keep_above = -1.0e300);
+// collective: every rank of the communicator calls with the same (replicated) matrix; the stages are
+// split across the ranks and the result is replicated again.
+void sym_eig(double* d_A, int64_t n, double* d_lam, bool vectors, double keep_above = -1.0e300, bool collective = false);
 // same with eigenvectors, solver forced: 0 library (cuSOLVER), 1 native (sytrd_kernel.cuh + stedc.cu)
 void sym_eig_select(double* d_A, int64_t n, double* d_lam, int solver);
 // backtransform.cu: Z (n x n) <- Q Z, Q = product of the Householder reflectors stored by the tridiagonalisation
@@ -104,6 +139,9 @@ struct SvtWorkspace {
 };
 // J = SVT_tau(A) written over A.  Returns rank(J).
 int64_t svt_inplace(SvtWorkspace& ws, double* d_A, int64_t n, double tau);
+// Collective variant for a block replicated on every rank (comm.h): on return the columns
+// [cb[rank], cb[rank+1]) of d_A hold J, the other columns are unspecified.
+int64_t svt_sharded(SvtWorkspace& ws, double* d_A, int64_t n, double tau, const std::vector<int64_t>& cb);
 
 // ---- drivers --------------------------------------------------------------------------
 struct AdmmResult {

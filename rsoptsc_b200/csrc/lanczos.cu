@@ -9,6 +9,7 @@
 #include <cmath>
 #include <functional>
 
+#include "comm.h"
 #include "gemm.h"
 #include "internal.h"
 #include "lanczos.h"
@@ -285,6 +286,8 @@ void Lanczos::advance(int more) {
   // Krylov space exhausted (beta ~ 0): truncate
   double scale = 0;
   for (int i = 0; i < steps; ++i) scale = std::max(scale, std::fabs(alpha[i]) + (i ? beta[i - 1] : 0.0));
+  for (int i = 0; i < steps; ++i)
+    if (!std::isfinite(beta[i]) || !std::isfinite(alpha[i])) nonfinite = true;
   for (int i = 0; i < steps; ++i) {
     if (!(beta[i] > 1e-14 * scale) || !std::isfinite(beta[i]) || !std::isfinite(alpha[i])) {
       steps = std::isfinite(alpha[i]) ? i + 1 : i;
@@ -326,6 +329,42 @@ void Lanczos::ritz_vectors(const std::vector<double>& S, const std::vector<int>&
 }
 
 // ---- spectral norm ------------------------------------------------------------------------
+// Certified top Ritz value of the running Lanczos process (shared by the two entry points below).
+// Returns sigma_1^2 >= 0, or NaN when the recurrence met non-finite values (NaN/Inf in the matrix):
+// the callers' finiteness checks then fail the run instead of reporting convergence.
+static double top_ritz_value(Lanczos& lz, double rel_tol) {
+  double prev = -1, cur = 0;
+  while (true) {
+    lz.advance(lz.steps == 0 ? 32 : 16);
+    if (lz.nonfinite) return std::nan("");
+    if (lz.steps == 0) return 0.0;
+    std::vector<double> theta, S;
+    lz.ritz(theta, S, /*last_row_only=*/true);
+    const int k = lz.steps;
+    cur = theta[k - 1];
+    if (std::isnan(cur)) return cur;
+    if (!(cur > 0)) return 0.0;
+    // residual bound of the top Ritz pair: |beta_k * s_k|
+    const double resid = std::fabs(lz.beta[k - 1] * S[k - 1]);
+    // Ritz value error <= min(resid, resid^2 / gap).  Ritz values within 0.1*rel_tol of the top are
+    // one cluster (their spread is below the requested accuracy); gap = distance to the rest.
+    double gap = cur;
+    for (int i = k - 2; i >= 0; --i)
+      if (cur - theta[i] > 0.1 * rel_tol * cur) { gap = cur - theta[i]; break; }
+    const double err = std::min(resid, resid * resid / gap);
+    const bool conv = err <= rel_tol * cur ||
+                      (prev > 0 && std::fabs(cur - prev) <= 1e-3 * rel_tol * cur && resid <= 1e-5 * cur);
+    if (conv || lz.exhausted) break;
+    if (lz.steps >= lz.max_steps) {
+      // not certified within the step budget: say so instead of returning a silently loose value
+      add_counter("lanczos_uncertified", 1.0);
+      break;
+    }
+    prev = cur;
+  }
+  return cur;
+}
+
 double spectral_norm(const double* d_M, int64_t rows, int64_t cols, double rel_tol) {
   Phase ph("lanczos");
   if (rows == 0 || cols == 0) return 0.0;
@@ -350,29 +389,39 @@ double spectral_norm(const double* d_M, int64_t rows, int64_t cols, double rel_t
       else            { mv.mul_n(v, tmp.p); mv.mul_t(tmp.p, w); }   // w = M^T (M v)
     });
   }
-  double prev = -1, cur = 0;
-  while (true) {
-    lz.advance(lz.steps == 0 ? 32 : 16);
-    if (lz.steps == 0) return 0.0;
-    std::vector<double> theta, S;
-    lz.ritz(theta, S, /*last_row_only=*/true);
-    const int k = lz.steps;
-    cur = theta[k - 1];
-    if (!(cur > 0)) return 0.0;
-    // residual bound of the top Ritz pair: |beta_k * s_k|
-    const double resid = std::fabs(lz.beta[k - 1] * S[k - 1]);
-    // Ritz value error <= min(resid, resid^2 / gap).  Ritz values within 0.1*rel_tol of the top are
-    // one cluster (their spread is below the requested accuracy); gap = distance to the rest.
-    double gap = cur;
-    for (int i = k - 2; i >= 0; --i)
-      if (cur - theta[i] > 0.1 * rel_tol * cur) { gap = cur - theta[i]; break; }
-    const double err = std::min(resid, resid * resid / gap);
-    const bool conv = err <= rel_tol * cur ||
-                      (prev > 0 && std::fabs(cur - prev) <= 1e-3 * rel_tol * cur && resid <= 1e-5 * cur);
-    if (conv || lz.exhausted || lz.steps >= lz.max_steps) break;
-    prev = cur;
+  return std::sqrt(top_ritz_value(lz, rel_tol));
+}
+
+double spectral_norm_colsharded(const double* d_M, int64_t rows, int64_t cols_local, double rel_tol) {
+  if (!sharded()) return spectral_norm(d_M, rows, cols_local, rel_tol);
+  Phase ph("lanczos");
+  if (rows == 0) return 0.0;
+  // Operator on the row side, M M^T = sum over ranks of M_r M_r^T (the ranks own disjoint columns).
+  // The recurrence runs replicated on bitwise identical data, so every rank takes the same decisions.
+  DenseMatvec mv;
+  DevBuf<double> tmp, B;
+  Lanczos lz;
+  if (rows <= 4096) {
+    B.alloc((size_t)rows * rows);
+    if (cols_local > 0) {
+      gram_AAt(d_M, rows, cols_local, B.p);
+      mirror_lower(B.p, rows);
+    } else {
+      B.zero(ctx().stream);
+    }
+    comm_allreduce_sum(B.p, (size_t)rows * rows);
+    mv.init(B.p, rows, rows);
+    lz.init(rows, 320, [&](const double* v, double* w) { mv.mul_t(v, w); });
+  } else {
+    if (cols_local > 0) mv.init(d_M, rows, cols_local);
+    tmp.alloc(std::max<int64_t>(cols_local, 1));
+    lz.init(rows, 320, [&](const double* v, double* w) {
+      if (cols_local > 0) { mv.mul_t(v, tmp.p); mv.mul_n(tmp.p, w); }
+      else RS_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * rows, ctx().stream));
+      comm_allreduce_sum(w, (size_t)rows);  // one n-vector per step
+    });
   }
-  return std::sqrt(cur);
+  return std::sqrt(top_ritz_value(lz, rel_tol));
 }
 
 }  // namespace rs

@@ -21,6 +21,7 @@ struct Lanczos {  // symmetric Lanczos with full reorthogonalisation on a device
   int64_t dim = 0;
   int max_steps = 0, steps = 0;
   bool exhausted = false;
+  bool nonfinite = false;  // NaN/Inf met in the recurrence (the operand holds non-finite values)
   std::function<void(const double*, double*)> op;  // w = B v (device pointers)
   DevBuf<double> Q, w, coef, d_alpha, d_beta, partial;
   std::vector<double> alpha, beta;

@@ -17,6 +17,7 @@
 // The O(n^3) work is entirely in the GEMMs; everything else is O(n^2).
 #include <cmath>
 
+#include "comm.h"
 #include "gemm.h"
 #include "internal.h"
 #include "stedc_core.h"
@@ -156,9 +157,10 @@ __global__ void __launch_bounds__(256) k_zhat(int k, const double* __restrict__ 
 __global__ void __launch_bounds__(128) k_build_M(int k, int nm, const double* __restrict__ dl, const int* __restrict__ org,
                                                  const double* __restrict__ tau, const double* __restrict__ zhat,
                                                  const int* __restrict__ idx_nd, const int* __restrict__ pos_nd,
-                                                 double* __restrict__ M) {
+                                                 double* __restrict__ M, int c_lo, int c_hi) {
   __shared__ double red[4];
   const int j = blockIdx.x, tid = threadIdx.x;
+  if (pos_nd[j] < c_lo || pos_nd[j] >= c_hi) return;  // multi-GPU: this rank builds the columns [c_lo, c_hi) of M only
   const int oj = org[j];
   const double tj = tau[j], dorg = dl[oj];
   double acc = 0;
@@ -176,15 +178,15 @@ __global__ void __launch_bounds__(128) k_build_M(int k, int nm, const double* __
 }
 
 __global__ void k_set_ones(int nd, int nm, const int* __restrict__ idx_def, const int* __restrict__ pos_def,
-                           double* __restrict__ M) {
+                           double* __restrict__ M, int c_lo, int c_hi) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < nd) M[idx_def[t] + (size_t)pos_def[t] * nm] = 1.0;
+  if (t < nd && pos_def[t] >= c_lo && pos_def[t] < c_hi) M[idx_def[t] + (size_t)pos_def[t] * nm] = 1.0;
 }
 
 // M <- R_1 (R_2 (... (R_m M))): the column rotations of the deflation step as row operations on M
-__global__ void k_rot_rows(int nm, const Rotation* __restrict__ rots, int nrot, double* __restrict__ M) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nm) return;
+__global__ void k_rot_rows(int nm, const Rotation* __restrict__ rots, int nrot, double* __restrict__ M, int c_lo, int c_hi) {
+  const int c = c_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= c_hi) return;
   double* col = M + (size_t)c * nm;
   for (int r = nrot - 1; r >= 0; --r) {
     const Rotation R = rots[r];
@@ -221,8 +223,23 @@ static void append(std::vector<char>& buf, const std::vector<T>& v, size_t& offs
 
 // Eigen-decomposition of the symmetric tridiagonal (d_d: n diagonal, d_e: n-1 off-diagonal, device).
 // d_lam (n, device): ascending eigenvalues; d_Z (n x n, ld n): eigenvectors; d_S1, d_S2: n x n scratch.
-void stedc_device(const double* d_d, const double* d_e, int64_t n64, double* d_lam, double* d_Z, double* d_S1, double* d_S2) {
+// collective (multi-GPU, every rank calls with the same d, e): the merges of stedc_split_min() rows and more are
+// split by OUTPUT columns -- rank q builds the columns q of M and forms Q_out[:, q] = diag(Q1, Q2) M[:, q]; the
+// column panels are all-gathered (Q stays replicated, so the next level's coupling rows are local).  The
+// levels below run replicated: they hold ~1/8 of the flops.
+static int64_t stedc_split_min() {
+  static int64_t v = -1;
+  if (v < 0) {
+    const char* e = getenv("RSOPTSC_STEDC_SPLIT_MIN");
+    v = e ? std::max<int64_t>(atoll(e), 2) : 3072;
+  }
+  return v;
+}
+
+void stedc_device(const double* d_d, const double* d_e, int64_t n64, double* d_lam, double* d_Z, double* d_S1, double* d_S2,
+                  bool collective) {
   Context& c = ctx();
+  collective = collective && sharded();
   const int n = (int)n64;
   RS_REQUIRE(n64 >= 1 && n64 <= 65535, "stedc: size out of range");
   std::vector<double> d(n), e(std::max(n - 1, 1), 0.0);
@@ -344,21 +361,38 @@ void stedc_device(const double* d_d, const double* d_e, int64_t n64, double* d_l
         continue;
       }
       double* M = d_S2;
-      RS_CUDA(cudaMemsetAsync(M, 0, sizeof(double) * (size_t)nm * nm, c.stream));
-      if (k > 0) {
-        const double* p_dl = (const double*)(dv_pack.p + offs[m].dl);
-        const double* p_zz = (const double*)(dv_pack.p + offs[m].zz);
-        RS_LAUNCH(k_zhat, (unsigned)cdiv(k, 8), 256, 0, k, p_dl, p_zz, dv_org.p + off, dv_tau.p + off, dv_zhat.p + off);
-        RS_LAUNCH(k_build_M, (unsigned)k, 128, 0, k, nm, p_dl, dv_org.p + off, dv_tau.p + off, dv_zhat.p + off,
-                  (const int*)(dv_pack.p + offs[m].idx_nd), (const int*)(dv_pack2.p + offs[m].pos_nd), M);
+      // output columns this rank forms: all of them, or its panel of a split merge
+      const bool split = collective && nm >= stedc_split_min();
+      std::vector<int64_t> mb;
+      int c_lo = 0, c_hi = nm;
+      if (split) {
+        mb = split_even(nm, comm().nranks, nm >= 4096 ? 128 : 1);
+        c_lo = (int)mb[comm().rank];
+        c_hi = (int)mb[comm().rank + 1];
       }
-      if (nd > 0) RS_LAUNCH(k_set_ones, (unsigned)cdiv(nd, 256), 256, 0, nd, nm, p_idx_def, p_pos_def, M);
-      if (nrot > 0)
-        RS_LAUNCH(k_rot_rows, (unsigned)cdiv(nm, 128), 128, 0, nm, (const Rotation*)(dv_pack.p + offs[m].rots), nrot, M);
-      // Q_in is block diagonal (the two children): two half-height GEMMs instead of one full one
-      const int n1 = blocks[2 * m].size, n2 = nm - n1;
-      gemm_nn_ld(Qblk, ldq, M, nm, Qout, ldq, n1, nm, n1);
-      gemm_nn_ld(Qblk + n1 + (long long)n1 * ldq, ldq, M + n1, nm, Qout + n1, ldq, n2, nm, n2);
+      const int wc = c_hi - c_lo;
+      if (wc > 0) {
+        RS_CUDA(cudaMemsetAsync(M + (size_t)c_lo * nm, 0, sizeof(double) * (size_t)nm * wc, c.stream));
+        if (k > 0) {
+          const double* p_dl = (const double*)(dv_pack.p + offs[m].dl);
+          const double* p_zz = (const double*)(dv_pack.p + offs[m].zz);
+          RS_LAUNCH(k_zhat, (unsigned)cdiv(k, 8), 256, 0, k, p_dl, p_zz, dv_org.p + off, dv_tau.p + off, dv_zhat.p + off);
+          RS_LAUNCH(k_build_M, (unsigned)k, 128, 0, k, nm, p_dl, dv_org.p + off, dv_tau.p + off, dv_zhat.p + off,
+                    (const int*)(dv_pack.p + offs[m].idx_nd), (const int*)(dv_pack2.p + offs[m].pos_nd), M, c_lo, c_hi);
+        }
+        if (nd > 0) RS_LAUNCH(k_set_ones, (unsigned)cdiv(nd, 256), 256, 0, nd, nm, p_idx_def, p_pos_def, M, c_lo, c_hi);
+        if (nrot > 0)
+          RS_LAUNCH(k_rot_rows, (unsigned)cdiv(wc, 128), 128, 0, nm, (const Rotation*)(dv_pack.p + offs[m].rots), nrot, M,
+                    c_lo, c_hi);
+        // Q_in is block diagonal (the two children): two half-height GEMMs instead of one full one
+        const int n1 = blocks[2 * m].size, n2 = nm - n1;
+        const double* Mc = M + (size_t)c_lo * nm;
+        double* Qo = Qout + (long long)c_lo * ldq;
+        gemm_nn_ld(Qblk, ldq, Mc, nm, Qo, ldq, n1, wc, n1);
+        gemm_nn_ld(Qblk + n1 + (long long)n1 * ldq, ldq, Mc + n1, nm, Qo + n1, ldq, n2, wc, n2);
+      }
+      // full-height columns travel: outside the diagonal block they are zero on every rank
+      if (split) comm_allgather_cols(Qn + (long long)off * ldq, ldq, mb);
     }
     std::vector<Block> next;
     for (size_t m = 0; m < nmerge; ++m) next.push_back({blocks[2 * m].off, blocks[2 * m].size + blocks[2 * m + 1].size});

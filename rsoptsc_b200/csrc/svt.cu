@@ -10,6 +10,7 @@
 // on the tensor cores by the split-integer GEMM of gemm_ozaki.cu.
 #include <cmath>
 
+#include "comm.h"
 #include "gemm.h"
 #include "internal.h"
 
@@ -70,6 +71,59 @@ int64_t svt_inplace(SvtWorkspace& ws, double* d_A, int64_t n, double tau) {
     gemm_nn(d_A, Vr, ws.T.p, n, r, n);                 // T = A V_r          (n x r)
     scale_columns(ws.T.p, n, r, ws.lam.p + r0);        // T *= diag(h_r)
     gemm_nt(ws.T.p, Vr, d_A, n, n, r);                 // J = T V_r^T        (n x n), over A
+  }
+  return r;
+}
+
+// ---- collective SVT of a block replicated on every rank (multi-GPU) ----------
+//   Gram           every rank forms one column panel of the lower triangle of G = A^T A (panels of
+//                  equal area), the panels are all-gathered over NVLink
+//   eigensolve     sym_eig(collective): fused multi-GPU tridiagonalisation, divide-and-conquer merges
+//                  and back-transformation split by columns
+//   reconstruction rank q forms its own columns of J only:  J[:, q] = A (V_r h V_r[q, :]^T)
+// so J never travels: the column-local ADMM kernels of rank q read exactly these columns.
+int64_t svt_sharded(SvtWorkspace& ws, double* d_A, int64_t n, double tau, const std::vector<int64_t>& cb) {
+  RS_REQUIRE(n <= 65535, "svt: block larger than 65,535 cells");
+  ws.ensure(n);
+  Context& c = ctx();
+  const Comm& cm = comm();
+  const int P = cm.nranks, rank = cm.rank;
+  {  // G = A^T A, lower triangle, one panel per rank
+    Phase ph("gram");
+    const std::vector<int64_t> gb = split_lower_triangle(n, P, 128);
+    const int64_t g0 = gb[rank], g1 = gb[rank + 1];
+    if (g1 > g0)  // rows g0.. of the panel: G[g0:, g0:g1] = A[:, g0:]^T A[:, g0:g1]
+      gemm_tn_ld(d_A + (size_t)g0 * n, n, d_A + (size_t)g0 * n, n, ws.G.p + g0 + (size_t)g0 * n, n, n - g0, g1 - g0, n);
+    comm_allgather_cols(ws.G.p, n, gb);
+  }
+  {
+    Phase ph("eig");
+    sym_eig(ws.G.p, n, ws.lam.p, /*vectors=*/true, tau * tau * (1.0 - 1e-9), /*collective=*/true);
+  }
+  std::vector<double> lam(n);
+  RS_CUDA(cudaMemcpyAsync(lam.data(), ws.lam.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+  RS_CUDA(cudaStreamSynchronize(c.stream));
+  std::vector<double> h(n, 0.0);
+  int64_t r0 = n;
+  for (int64_t i = n - 1; i >= 0; --i) {
+    const double sig = lam[i] > 0 ? std::sqrt(lam[i]) : 0.0;
+    if (sig > tau) { h[i] = 1.0 - tau / sig; r0 = i; } else break;
+  }
+  const int64_t r = n - r0;
+  const int64_t c0 = cb[rank], c1 = cb[rank + 1], w = c1 - c0;
+  if (r == 0) {
+    if (w > 0) RS_CUDA(cudaMemsetAsync(d_A + (size_t)c0 * n, 0, sizeof(double) * n * w, c.stream));
+    return 0;
+  }
+  Phase ph("recon");
+  if (w > 0) {
+    const double* Vr = ws.G.p + (size_t)r0 * n;
+    RS_CUDA(cudaMemcpyAsync(ws.lam.p + r0, h.data() + r0, sizeof(double) * r, cudaMemcpyHostToDevice, c.stream));
+    copy_scale_columns(Vr, n, r, ws.lam.p + r0, ws.T.p);                  // T = V_r diag(h)          (n x r)
+    DevBuf<double> Bq((size_t)n * w), Jq((size_t)n * w);
+    gemm_nt_ld(ws.T.p, n, Vr + c0, n, Bq.p, n, n, w, r);                  // B[:, q] = T V_r[q, :]^T  (n x w)
+    gemm_nn_ld(d_A, n, Bq.p, n, Jq.p, n, n, w, n);                        // J[:, q] = A B[:, q]
+    RS_CUDA(cudaMemcpyAsync(d_A + (size_t)c0 * n, Jq.p, sizeof(double) * n * w, cudaMemcpyDeviceToDevice, c.stream));
   }
   return r;
 }
