@@ -8,8 +8,10 @@ genes x cells matrix (BASELINE.json configs[1]: 10,000 cells x 2,000 genes on 1 
   value  whole-job cells/s with the input matrix resident in HBM (rsoptsc_*_dev entry points)
   e2e    the same through the host-buffer C ABI (rsoptsc_similarity + rsoptsc_nmf_lee): pinned
          host input, host<->device copies inside the timed region
-  N > 1  (torchrun) N independent replicas, one matrix per GPU, no data-path collective
-         ("replicas only" this round) -> weak scaling
+  N > 1  (torchrun) ONE problem split across the N GPUs inside the library (librsoptsc_b200's own NCCL
+         communicator: column blocks of the ADMM state, collective SVT with the Gram / eigensolver /
+         reconstruction split across the ranks, NCCL allreduce of the stop-rule Grams) -> strong scaling;
+         --replicas keeps the round-1 mode (N independent matrices, weak scaling)
   --impl reference   the CPU oracle (numpy/OpenBLAS restatement of the R code, all host
          threads) on a bounded sample of the same workload; rank 0 only
 Prints ONE JSON line on rank 0.
@@ -31,7 +33,7 @@ M_GENES = 2000
 N_CELLS = 10000
 LAMBDA = 0.5
 RANK = 10
-CPU_SAMPLE_CELLS = 500
+CPU_SAMPLE_CELLS = 1000   # BASELINE.json configs[0]: the reference's own CPU-runnable case, run in full
 METRIC = "SimilarityM+ClusterCells throughput"
 UNIT = "cells/s"
 
@@ -99,48 +101,79 @@ def cpu_oracle_sample(data, cells, steps=1, threads=None):
     return times
 
 
-def best_cpu_threads(data, cells):
-    """torchrun pins OMP_NUM_THREADS=1 and an oversubscribed OpenBLAS can be slower than one thread
-    at this size: time the sample with all host threads and with one, keep the faster setting."""
+def best_cpu_threads(data, cells=300):
+    """torchrun pins OMP_NUM_THREADS=1 and an oversubscribed OpenBLAS can be slower than a few threads:
+    a short probe (300 cells) picks the BLAS thread count among {all, half, 8, 1} host threads."""
     ncpu = os.cpu_count() or 1
-    cand = sorted({1, ncpu})
+    cand = sorted({1, min(8, ncpu), max(1, ncpu // 2), ncpu}, reverse=True)
     best = None
     for th in cand:
-        t = cpu_oracle_sample(data, cells, threads=th)[0]
+        t = min(cpu_oracle_sample(data, cells, steps=2, threads=th))
         if best is None or t < best[1]:
             best = (th, t)
     return best
 
 
-def run_reference(args, rank):
+def bench_config(args, world):
+    """The workload both arms describe (identical dict in the GPU line and in the reference line)."""
+    if args.replicas and world > 1:
+        par = "replicas x%d (no data-path collective)" % world
+    elif world > 1:
+        par = ("1 problem over %d GPUs: cells (columns of Z, E, Y1, XXZ, Y3, J) sharded, SVT collective (Gram panels "
+               "+ eigensolver stages + reconstruction split, NCCL all-gather / allreduce over NVLink)" % world)
+    else:
+        par = "1 GPU"
+    return {"workload": workload_name(args), "cells": args.cells, "genes": args.genes, "lambda": LAMBDA,
+            "nmf_rank": RANK, "parallelism": par,
+            "headline_config_measured": args.cells >= 50000,
+            "headline_note": ("BASELINE.json's metric is quoted at 50,000 cells (configs[2]); one step of it takes "
+                              "minutes on one B200 (profiles/), so the driver-sized run (--steps 20) uses configs[1]; "
+                              "`python bench.py --cells 50000 --steps 1 --warmup 0` runs configs[2] with this same code"),
+            "l2": "working set (%.1f GB of dense n x n state) exceeds the 126 MB L2" % (5 * 8e-9 * args.cells * args.cells)}
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the CPU oracle (numpy/OpenBLAS restatement of R/SimilarityM.R + R/Clustering.R; R itself
+    is not installable here), all useful host threads.  Every step is the SAME pipeline as the GPU arm's step on a
+    bounded sample of the workload: the first `cells` columns of the seed-0 matrix.  cells = 1,000 (BASELINE.json
+    configs[0] in full) when steps x its time fits ~6 minutes, else 700 / 500 -- stated in cpu_baseline.sample."""
     if rank != 0:
         return
     from rsoptsc_b200.synthetic import synthetic_lognorm
+    data, _ = synthetic_lognorm(args.genes, 2000, seed=0)
+    threads, t300 = best_cpu_threads(data)          # doubles as BLAS warm-up
     cells = args.cpu_cells
-    data, _ = synthetic_lognorm(args.genes, max(cells, 16), seed=0)
-    threads, _ = best_cpu_threads(data, cells)  # doubles as the warm-up pass; picks 1 vs all host threads
+    if not args.cpu_cells_fixed:
+        for cand in (1000, 700, 500):
+            cells = cand
+            if args.steps * t300 * (cand / 300.0) ** 2.6 <= 360.0:
+                break
+    for _ in range(min(args.warmup, 1)):            # warm-up steps: one short pass (page-in, thread pool)
+        cpu_oracle_sample(data, min(cells, 300), threads=threads)
     times = cpu_oracle_sample(data, cells, steps=args.steps, threads=threads)
     t = float(np.mean(times))
     value = cells / t
-    sample = ("first %d cells x %d genes of the seed-0 synthetic matrix, full SimilarityM (literal full-SVD norms as "
-              "in R) + ClusterCells k=%d; cost grows ~n^3 so cells/s at %d cells would be far lower"
-              % (cells, args.genes, RANK, args.cells))
+    sample = ("each step = full SimilarityM (literal full-SVD norms as in R) + ClusterCells k=%d on the first %d cells x "
+              "%d genes of the seed-0 synthetic matrix (%s), %d BLAS threads of %d host CPUs; cost grows ~n^2.6-n^3, so "
+              "cells/s at %d cells is far lower (not measured: hours)"
+              % (RANK, cells, args.genes, "BASELINE.json configs[0] in full" if cells == 1000 else "bounded sample",
+                 threads, os.cpu_count() or 1, args.cells))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "cells": args.cells, "genes": args.genes, "lambda": LAMBDA,
-                   "nmf_rank": RANK, "reference_arm": "numpy/OpenBLAS oracle (R is not installable here)"},
+        "scaling": "weak" if args.replicas else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": bench_config(args, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "host_cpus": os.cpu_count()},
+                         "host_cpus": os.cpu_count(), "sample_cells": cells,
+                         "reference_arm": "numpy/OpenBLAS oracle (R is not installable here)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 def workload_name(args):
-    return ("configs[1]: %d cells x %d genes synthetic log-normalised, SimilarityM (lambda=%.2g, in-library PCA "
-            "embedding) + ClusterCells (NMF lee/nndsvd, k=%d) on 1 B200 per replica"
-            % (args.cells, args.genes, LAMBDA, RANK))
+    cfg = {1000: "configs[0]", 10000: "configs[1]", 50000: "configs[2]"}.get(args.cells, "custom")
+    return ("%s: %d cells x %d genes synthetic log-normalised, SimilarityM (lambda=%.2g, in-library PCA "
+            "embedding) + ClusterCells (NMF lee/nndsvd, k=%d)" % (cfg, args.cells, args.genes, LAMBDA, RANK))
 
 
 # algorithmic bytes per launch of the HBM-bound kernels we own (DESIGN.md section 4)
@@ -171,18 +204,22 @@ def main():
     ap.add_argument("--impl", default="native")
     ap.add_argument("--cells", type=int, default=N_CELLS)
     ap.add_argument("--genes", type=int, default=M_GENES)
-    ap.add_argument("--cpu-cells", type=int, default=CPU_SAMPLE_CELLS)
+    ap.add_argument("--cpu-cells", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: independent matrices per GPU (weak scaling)")
     args = ap.parse_args()
+    args.cpu_cells_fixed = args.cpu_cells is not None
+    if args.cpu_cells is None:
+        args.cpu_cells = CPU_SAMPLE_CELLS
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
         return
 
     import torch
     import torch.distributed as dist
-    from rsoptsc_b200 import _lib, api
+    from rsoptsc_b200 import _lib, api, parallel
     from rsoptsc_b200.synthetic import synthetic_lognorm
 
     if not torch.cuda.is_available():
@@ -190,7 +227,16 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    _lib.init(local_rank)
+    lib = _lib.init(local_rank)
+    shard = world > 1 and not args.replicas
+    if shard:
+        # the library's own NCCL communicator (no torch inside the package): rank 0's unique id travels over
+        # the process group torchrun already gave this script
+        def bcast(payload):
+            box = [payload]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        parallel.init_comm(rank, world, device=local_rank, broadcast=bcast)
     m, n = args.genes, args.cells
 
     def barrier():
@@ -199,8 +245,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # one independent matrix per replica (seed = rank)
-    data, _ = synthetic_lognorm(m, n, seed=rank)
+    # strong scaling: the SAME matrix on every rank (inputs are replicated, the state is sharded);
+    # --replicas: one independent matrix per rank
+    data, _ = synthetic_lognorm(m, n, seed=0 if not args.replicas else rank)
     d_data = api.DeviceBuffer.from_host(data)
     d_W = api.DeviceBuffer(n * n * 8)
     info = {}
@@ -214,6 +261,7 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     api.timers(True)
+    comm0 = parallel.comm_info() if shard else None
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:  # one nvidia-smi poller per job is enough (rank 0's GPU)
@@ -229,9 +277,10 @@ def main():
     launches = api.kernel_launches() - launches0
     t_dev = api.phase_ms("step") / 1e3
     phases = api.phase_report()
-    oz_flops = _lib.load().rsoptsc_counter(b"ozaki_fp64_flops")
-    oz_iops = _lib.load().rsoptsc_counter(b"ozaki_int8_ops")
-    sytrd_bytes = _lib.load().rsoptsc_counter(b"sytrd_panel_bytes")
+    comm1 = parallel.comm_info() if shard else None
+    oz_flops = lib.rsoptsc_counter(b"ozaki_fp64_flops")
+    oz_iops = lib.rsoptsc_counter(b"ozaki_int8_ops")
+    sytrd_bytes = lib.rsoptsc_counter(b"sytrd_panel_bytes")
     api.timers(False)
 
     # end to end through the host-buffer C ABI, pinned host input/output
@@ -263,6 +312,26 @@ def main():
     if sampler.is_alive():
         sampler.join(timeout=2)
 
+    # the same pipeline at the size the CPU oracle is timed on (configs[0], 1,000 cells): the one like-for-like
+    # GPU / CPU pair of this report (rank 0, N = 1 only; untimed part of the run)
+    same_size = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.cpu_cells < n:
+        nc = args.cpu_cells
+        sub = np.asfortranarray(data[:, :nc])
+        d_sub = api.DeviceBuffer.from_host(sub)
+        d_Ws = api.DeviceBuffer(nc * nc * 8)
+
+        def step_small():
+            api.SimilarityM_dev(LAMBDA, d_sub, m, nc, d_W=d_Ws)
+            api.nmf_lee_dev(d_Ws, nc, RANK)
+        step_small()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            step_small()
+        lib.rsoptsc_dev_sync()
+        same_size = {"cells": nc, "gpu_s_per_step": (time.perf_counter() - t0) / 3}
+
     # max over ranks
     tt = torch.tensor([t_dev, e2e["t"] if e2e else 0.0, t_wall], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -277,91 +346,97 @@ def main():
             pass
         hbm_peak, peak_src = (peaks.get("hbm_gbs"), "MEASURED_PEAKS.json hbm_gbs") if peaks.get("hbm_gbs") else \
             (6650.0, "fallback (B200_PROFILING.md)")
+        bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
+        bf16_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks.get("bf16_tflops_sustained") else \
+            "fallback (B200_PROFILING.md)"
         nnz = n * info.get("K", 30)
-        # dominant kernel among the kernels this repo owns (cuSOLVER/cuBLAS phases reported in `phases`)
-        own = [(p, v) for p, v in phases.items() if own_kernel_bytes(p, m, n, nnz)]
         roof = None
         oz = phases.get("ozaki_gemm")
         sy = phases.get("sytrd_panel")
+
+        def ozaki_roof():
+            pairs = max(oz_iops / max(oz_flops, 1.0), 1.0)
+            osec = oz["ms"] / 1e3
+            return {"kernel": "k_ozaki_gemm<8> (tcgen05.mma kind::i8, FP64-equivalent)", "bound": "tensor",
+                    "achieved": oz_flops / osec / 1e12, "peak": 2.0 * bf16 / pairs, "unit": "TFLOP/s",
+                    "frac": (oz_flops / osec / 1e12) / (2.0 * bf16 / pairs),
+                    "traffic": 13.43e9,
+                    "traffic_note": "dram read+write of ONE launch, the n=10000 Gram, from ncu --set full "
+                                    "(profiles/r1_ozaki_gemm_ncu_full.csv): tensor-bound, DRAM at 11 %",
+                    "int8_tops_achieved": oz_iops / osec / 1e12, "int8_tops_peak": 2.0 * bf16,
+                    "peak_source": "2 x %s (int8 runs at twice the bf16 rate) / %d int8 slice-pair MMAs per FP64 MAC"
+                                   % (bf16_src, round(pairs)),
+                    "share_of_step": osec / t_dev, "launches": oz["calls"], "cublas_fp64_reference_tflops": 35.6}
+
         if sy and sy["ms"] > 0 and (not oz or sy["ms"] >= oz["ms"]):
-            # dominant kernel: the cooperative panel kernel of the tridiagonalisation (symmetric
-            # eigensolver of every SVT).  HBM-bound: its product phase reads the lower triangle of the
-            # trailing matrix once per column; algorithmic bytes = sum over columns of 4 (n - j - 1)^2.
+            # dominant kernel: the cooperative panel kernel of the tridiagonalisation (symmetric eigensolver of
+            # every SVT).  HBM-bound: its product phase reads the lower triangle of the trailing matrix once per
+            # column; algorithmic bytes = sum over columns of 4 (n - j - 1)^2 (this rank's share when sharded).
             secs = sy["ms"] / 1e3
             achieved = sytrd_bytes / secs / 1e9
-            roof = {"kernel": "k_latrd_panel (Householder tridiagonalisation, 64-column panels)", "bound": "hbm",
-                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": SYTRD_NCU_TRAFFIC,
-                    "traffic_note": SYTRD_NCU_NOTE,
+            roof = {"kernel": "k_latrd_panel%s (Householder tridiagonalisation, 64-column panels)" % ("_mg" if shard else ""),
+                    "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": SYTRD_NCU_TRAFFIC if not shard else None,
+                    "traffic_note": SYTRD_NCU_NOTE if not shard else "rank 0's share of the lower triangles",
                     "peak_source": peak_src, "share_of_step": secs / t_dev, "launches": sy["calls"],
                     "algorithmic_bytes_per_launch": sytrd_bytes / max(sy["calls"], 1)}
             if oz and oz["ms"] > 0:
-                bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
-                pairs = max(oz_iops / max(oz_flops, 1.0), 1.0)
-                osec = oz["ms"] / 1e3
-                roof["second_kernel"] = {
-                    "kernel": "k_ozaki_gemm<8> (tcgen05.mma kind::i8, FP64-equivalent)", "bound": "tensor",
-                    "achieved": oz_flops / osec / 1e12, "peak": 2.0 * bf16 / pairs, "unit": "TFLOP/s",
-                    "frac": (oz_flops / osec / 1e12) / (2.0 * bf16 / pairs), "share_of_step": osec / t_dev,
-                    "launches": oz["calls"], "cublas_fp64_reference_tflops": 35.6}
+                roof["second_kernel"] = ozaki_roof()
         elif oz and oz["ms"] > 0:
-            # dominant kernel this repo owns: the tcgen05 kind::i8 split-integer GEMM (Gram + the two
-            # reconstruction GEMMs of every SVT).  achieved = FP64-equivalent flops / device time;
-            # peak = int8 tensor peak (2 x measured dense bf16) / 36 slice-pair MMAs per FP64 MAC.
-            bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
-            bf16_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks.get("bf16_tflops_sustained") else \
-                "fallback (B200_PROFILING.md)"
-            flops, iops = oz_flops, oz_iops
-            secs = oz["ms"] / 1e3
-            pairs = max(iops / max(flops, 1.0), 1.0)
-            roof = {"kernel": "k_ozaki_gemm<8> (tcgen05.mma kind::i8, FP64-equivalent)", "bound": "tensor",
-                    "achieved": flops / secs / 1e12, "peak": 2.0 * bf16 / pairs, "unit": "TFLOP/s",
-                    "frac": (flops / secs / 1e12) / (2.0 * bf16 / pairs),
-                    "traffic": 13.43e9,
-                    "traffic_note": "dram read+write of ONE launch, the n=10000 Gram, from ncu --set full "
-                                    "(profiles/r1_ozaki_gemm_ncu_full.csv); its operands are 0.8 GB of int8 slices + "
-                                    "0.4 GB FP64 output, re-read per tile row/column through L2 (11 % of DRAM "
-                                    "bandwidth: the kernel is tensor-bound, tensor pipe active 65 %)",
-                    "int8_tops_achieved": iops / secs / 1e12, "int8_tops_peak": 2.0 * bf16,
-                    "frac_of_nominal_int8_4500_tops": iops / secs / 1e12 / 4500.0,
-                    "peak_source": "2 x %s (int8 runs at twice the bf16 rate) / %d int8 slice-pair MMAs per FP64 MAC"
-                                   % (bf16_src, round(pairs)),
-                    "share_of_step": secs / t_dev, "launches": oz["calls"],
-                    "cublas_fp64_reference_tflops": 35.6}
-        elif own:
-            name, v = max(own, key=lambda kv: kv[1]["ms"])
-            per_launch_s = v["ms"] / 1e3 / max(v["calls"], 1)
-            achieved = own_kernel_bytes(name, m, n, nnz) / per_launch_s / 1e9
-            roof = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                    "share_of_step": v["ms"] / 1e3 / t_dev, "launches": v["calls"]}
+            roof = ozaki_roof()
+        else:
+            own = [(p, v) for p, v in phases.items() if own_kernel_bytes(p, m, n, nnz)]
+            if own:
+                name, v = max(own, key=lambda kv: kv[1]["ms"])
+                per_launch_s = v["ms"] / 1e3 / max(v["calls"], 1)
+                achieved = own_kernel_bytes(name, m, n, nnz) / per_launch_s / 1e9
+                roof = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "share_of_step": v["ms"] / 1e3 / t_dev, "launches": v["calls"]}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            cpu_threads, t_cpu = best_cpu_threads(data, args.cpu_cells)
-            cpu = {"value": args.cpu_cells / t_cpu, "unit": UNIT, "cores": cpu_threads, "host_cpus": os.cpu_count(),
-                   "kind": "port",
-                   "sample": "first %d cells x %d genes of the same matrix, oracle SimilarityM (literal full-SVD norms) "
-                             "+ ClusterCells k=%d, %.1f s; cost ~n^3, so this overstates CPU cells/s at %d cells"
-                             % (args.cpu_cells, m, RANK, t_cpu, n), "seconds": t_cpu}
-        value = world * n * args.steps / t_dev
+            sdata = data if n >= 300 else synthetic_lognorm(m, 300, seed=0)[0]
+            cpu_threads, _ = best_cpu_threads(sdata, min(300, n))
+            nc = min(args.cpu_cells, n)
+            t_cpu = cpu_oracle_sample(data, nc, threads=cpu_threads)[0]
+            cpu = {"value": nc / t_cpu, "unit": UNIT, "cores": cpu_threads, "host_cpus": os.cpu_count(), "kind": "port",
+                   "sample": "first %d cells x %d genes of the same matrix (%s), oracle SimilarityM (literal full-SVD "
+                             "norms as in R) + ClusterCells k=%d once: %.1f s; cost ~n^3, so this overstates CPU cells/s "
+                             "at %d cells" % (nc, m, "BASELINE.json configs[0] in full" if nc == 1000 else "bounded sample",
+                                              RANK, t_cpu, n),
+                   "seconds": t_cpu, "sample_cells": nc,
+                   "extrapolated_seconds_at_bench_size": t_cpu * (n / nc) ** 3,
+                   "extrapolation": "n^3 law from the one measured point; EXTRAPOLATED, not measured"}
+            if same_size:
+                same_size.update(cpu_s_per_step=t_cpu, gpu_cells_per_s=nc / same_size["gpu_s_per_step"],
+                                 cpu_cells_per_s=nc / t_cpu, gpu_over_cpu=t_cpu / same_size["gpu_s_per_step"],
+                                 note="same pipeline, same %d-cell input, same box: the like-for-like GPU/CPU pair" % nc)
+        value = (world if args.replicas else 1) * n * args.steps / t_dev
+        cfg = bench_config(args, world)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "cells": n, "genes": m, "lambda": LAMBDA, "nmf_rank": RANK,
-                       "K": info.get("K"), "admm_iters": info.get("iters"), "nmf_iters": info.get("nmf_iters"),
-                       "parallelism": "replicas x%d (no data-path collective)" % world,
-                       "l2": "working set (%.1f GB dense state per replica) exceeds the 126 MB L2" % (5 * 8e-9 * n * n)},
+            "scaling": "weak" if args.replicas else "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfg,
             "wall_s_per_step": t_wall / args.steps,
-            "e2e": ({"value": world * n * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
-                     "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": t_e2e / args.steps * 1e3} if e2e else None),
+            "e2e": ({"value": (world if args.replicas else 1) * n * args.steps / t_e2e, "unit": UNIT,
+                     "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                     "ms_per_step": t_e2e / args.steps * 1e3} if e2e else None),
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
+            "extra": {"K": info.get("K"), "admm_iters": info.get("iters"), "nmf_iters": info.get("nmf_iters"),
+                      "E": info.get("E"), "same_size_as_cpu_baseline": same_size,
+                      "comm": ({"nranks": comm1["nranks"], "peer_mapped_exchange": comm1["p2p"],
+                                "collectives_per_step": (comm1["collectives"] - comm0["collectives"]) / args.steps,
+                                "GB_per_step_rank0": (comm1["bytes"] - comm0["bytes"]) / 1e9 / args.steps}
+                               if shard else None)},
             "phases_ms_per_step": {p: round(v["ms"] / args.steps, 3) for p, v in phases.items() if p not in ("e2e",)},
         }
         print(json.dumps(out))
+    if shard:
+        parallel.finalize_comm()
     if world > 1:
         dist.destroy_process_group()
 

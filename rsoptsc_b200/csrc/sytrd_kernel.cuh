@@ -311,7 +311,7 @@ __device__ __forceinline__ double row_combine(double acc, int sub, int jj, const
   return acc;
 }
 
-__global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
+static __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
   __shared__ double s_tmp[32], s_out[2], s_bc[2];
   __shared__ double s_p1[NB], s_p2[NB];      // W^T v, V^T v
   __shared__ double s_vr[NB], s_wr[NB];      // row j+1 of V and W
@@ -614,7 +614,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel(Params P) {
 #undef RS_PROF
 }
 
-__global__ void k_restore_subdiag(double* A, long long lda, int n, const double* e, double* d) {
+static __global__ void k_restore_subdiag(double* A, long long lda, int n, const double* e, double* d) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n - 1) A[(i + 1) + (long long)i * lda] = e[i];
   if (i == n - 1) d[n - 1] = A[(long long)(n - 1) * lda + (n - 1)];
