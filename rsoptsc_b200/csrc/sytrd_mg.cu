@@ -8,13 +8,11 @@
 namespace rs {
 
 static int64_t mg_min_n() {
-  static int64_t t = -1;
-  if (t < 0) {
-    // below ~3,000 rows a column streams in under 2 us per rank: the NVLink exchange costs more than it saves
-    const char* e = getenv("RSOPTSC_SYTRD_MG_MIN_N");
-    t = e ? atoll(e) : 3000;
-    if (t < 2 * sytrd::NB) t = 2 * sytrd::NB;
-  }
+  // the exchange adds ~3 us per column; the product phase of a column takes 14.5 us (n / 7,954)^2 on one GPU and
+  // 1/P of that on P: below these sizes the exchange costs more than it saves
+  const char* e = getenv("RSOPTSC_SYTRD_MG_MIN_N");
+  int64_t t = e ? atoll(e) : (comm().nranks >= 4 ? 4000 : 6000);
+  if (t < 2 * sytrd::NB) t = 2 * sytrd::NB;
   return t;
 }
 
@@ -29,10 +27,20 @@ void sytrd_mg_run(double* d_A, int64_t n, double* d_d, double* d_e, double* d_ta
   Context& c = ctx();
   Comm& cm = comm();
   RS_REQUIRE(cm.p2p && cm.xchg_doubles >= sytrd::mg_region_doubles(n, cm.nranks), "sytrd_mg: exchange regions not mapped");
-  // arrival counters restart at zero; nobody may signal a region before its owner has cleared it
-  RS_CUDA(cudaMemsetAsync(cm.xchg[cm.rank], 0, sizeof(double) * sytrd::XCH_HDR, c.stream));
-  RS_CUDA(cudaStreamSynchronize(c.stream));
-  comm_barrier();
+  RS_REQUIRE(n <= 65535, "sytrd_mg: more than 65,535 rows");
+  // packet flags = epoch << 16 | column + 1: a fresh epoch per factorisation (identical on every rank: the library is
+  // SPMD), the regions cleared whenever the 16-bit counter wraps or the regions were re-created
+  static unsigned epoch = 0;
+  static const double* epoch_region = nullptr;
+  if (epoch_region != cm.xchg[cm.rank]) { epoch = 0; epoch_region = cm.xchg[cm.rank]; }
+  if (++epoch > 65535u) epoch = 1;
+  if (epoch == 1) {
+    RS_CUDA(cudaStreamSynchronize(c.stream));
+    comm_barrier();  // no peer is still writing packets of an earlier factorisation
+    RS_CUDA(cudaMemsetAsync(cm.xchg[cm.rank], 0, sizeof(double) * cm.xchg_doubles, c.stream));
+    RS_CUDA(cudaStreamSynchronize(c.stream));
+    comm_barrier();  // nobody writes into a region before its owner has cleared it
+  }
   DevBuf<double> work(sytrd::workspace_doubles(n));
   sytrd::Hooks hooks;
   Phase* panel_phase = nullptr;
@@ -47,11 +55,11 @@ void sytrd_mg_run(double* d_A, int64_t n, double* d_d, double* d_e, double* d_ta
   };
   int64_t launches = 0;
   const int grid = std::min(c.sm_count, sytrd::MAX_GRID);  // identical on every rank (arrival targets count CTAs)
-  RS_CUDA(sytrd::run_mg(c.cublas, c.stream, d_A, n, n, d_d, d_e, d_tau, work.p, cm.nranks, cm.rank, cm.xchg, grid,
+  RS_CUDA(sytrd::run_mg(c.cublas, c.stream, d_A, n, n, d_d, d_e, d_tau, work.p, cm.nranks, cm.rank, cm.xchg, epoch, grid,
                         &launches, &hooks));
   g_launches.fetch_add(launches, std::memory_order_relaxed);
   cm.collectives += (n + sytrd::NB - 1) / sytrd::NB;  // one fused compute + exchange kernel per panel
-  cm.collective_bytes += 8.0 * (double)n * (double)n / 2.0 * (double)(cm.nranks - 1);  // y vectors pushed to the peers
+  cm.collective_bytes += 16.0 * (double)n * (double)n / 2.0 * (double)(cm.nranks - 1);  // 16-byte y packets pushed to the peers
 }
 
 }  // namespace rs

@@ -10,9 +10,12 @@
 //     round-robin.
 //   * After its product phase a rank reduces its OWN partial sums to one n'-vector (rows it touched, zeros
 //     elsewhere) and writes that vector -- plus its share of W^T v, V^T v and v^T A v -- straight into the
-//     exchange region of every rank with NVLink stores (8 n' P bytes out per column), then signals one
-//     arrival counter per rank with red.release.sys; every CTA polls its own rank's counter (ld.acquire.sys).
-//     Buffers alternate with the column parity, the counter is monotonic over the whole factorisation.
+//     exchange region of every rank with NVLink stores.  Every value travels as one 16-byte flag-with-data
+//     packet {lo, flag, hi, flag} (flag = solve epoch << 16 | column + 1; each 8-byte half is delivered
+//     atomically), and the row phase of the receiver simply spins on the packets it needs: no fence, no arrival
+//     counter, no second NVLink round trip (a first version with __threadfence_system + red.release.sys
+//     counters cost ~14 us per column at 7,954 rows, more than the product phase it saved on 2 GPUs).
+//     Buffers alternate with the column parity: a rank can run at most one column ahead of a peer.
 //   * The row phase (w, the final W column, the update of column j+1) runs replicated on bitwise identical
 //     sums, so the panel, the reflectors and d/e/tau stay identical on all ranks and the rank-2NB trailing
 //     update needs no communication at all.
@@ -24,20 +27,44 @@ namespace rs {
 namespace sytrd {
 
 constexpr int MG_MAX_RANKS = 8;  // == TPR: one lane of a row group per rank in the row phase
-constexpr int XCH_HDR = 32;      // doubles at the head of an exchange region (arrival counter)
+constexpr int XCH_HDR = 32;      // doubles at the head of an exchange region (reserved)
 static_assert(MG_MAX_RANKS <= TPR, "row phase reads one rank per lane of a row group");
 
 struct MgParams {
   Params b;
   int nranks, rank;
   double* xch[MG_MAX_RANKS];  // exchange region of every rank as mapped in this process
-  long long xlen;             // doubles per exchanged vector: y (n) | W^T v (NB) | V^T v (NB) | v^T A v | pad
+  long long xlen;             // packets per exchanged vector: y (n) | W^T v (NB) | V^T v (NB) | v^T A v | pad
+  unsigned epoch;             // solve counter (1 .. 65535), upper half of every packet flag
 };
 inline long long mg_xlen(int64_t n) { return (n + 2 * NB + 2 + 31) / 32 * 32; }
-inline size_t mg_region_doubles(int64_t n, int nranks) { return (size_t)XCH_HDR + 2 * (size_t)nranks * (size_t)mg_xlen(n); }
+// two parities x nranks sources x xlen packets of 16 bytes
+inline size_t mg_region_doubles(int64_t n, int nranks) { return (size_t)XCH_HDR + 4 * (size_t)nranks * (size_t)mg_xlen(n); }
 
-__device__ __forceinline__ double* mg_vec(double* region, int par, int src, int nranks, long long xlen) {
-  return region + XCH_HDR + (long long)(par * nranks + src) * xlen;
+__device__ __forceinline__ uint4* mg_vec(double* region, int par, int src, int nranks, long long xlen) {
+  return reinterpret_cast<uint4*>(region + XCH_HDR) + (long long)(par * nranks + src) * xlen;
+}
+// flag-with-data packet: both 8-byte halves carry the flag, so a reader that sees both flags has both halves
+__device__ __forceinline__ void ll_store(uint4* slot, double v, unsigned flag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(slot), "r"((unsigned)b), "r"(flag),
+               "r"((unsigned)(b >> 32)), "r"(flag)
+               : "memory");
+}
+__device__ __forceinline__ double ll_load(const uint4* slot, unsigned flag) {
+  unsigned lo, f0, hi, f1, spins = 0;
+  unsigned long long t_start = 0;
+  for (;;) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(slot) : "memory");
+    if (f0 == flag && f1 == flag) break;
+    if ((++spins & 0x3fffu) == 0) {  // a lost peer must fault, not hang the device: 20 s of wall clock
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t_start == 0) t_start = now;
+      else if (now - t_start > 20000000000ull) __trap();
+    }
+  }
+  return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
 
 // Unit map of one rank for one column: its block rows [b0, b1) of the trailing triangle (relative to Bmin),
@@ -174,7 +201,6 @@ static __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel_mg(MgParams Q
   const int gwarp = blockIdx.x * (THREADS / 32) + warp;
   const long long nwarps = (long long)nblocks * (THREADS / 32);
   double* xloc = Q.xch[rank];
-  unsigned* ctr_local = reinterpret_cast<unsigned*>(xloc);
 
   double* sbuf = s_stage + (size_t)warp * STAGE_DOUBLES;
   long long staged = -1;
@@ -196,6 +222,7 @@ static __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel_mg(MgParams Q
   for (int jj = 0; jj < P.pw; ++jj) {
     const int j = P.j0 + jj;
     const int par = j & 1;
+    const unsigned flag = (Q.epoch << 16) | (unsigned)((j + 1) & 0xffff);
     const double* ab = P.abuf + (size_t)(j & 1) * n;
     double* abn = P.abuf + (size_t)((j + 1) & 1) * n;
     const MgMap um = mg_map(NR, rank, j, jj, n, P.mB, nwarps);
@@ -350,9 +377,9 @@ static __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel_mg(MgParams Q
       pa += __shfl_xor_sync(0xffffffffu, pa, 1);
       pa += __shfl_xor_sync(0xffffffffu, pa, 2);
       if (c4 == 0 && q < 2 * jj)
-        for (int r = 0; r < NR; ++r) mg_vec(Q.xch[r], par, rank, NR, xlen)[n + q] = pa;
+        for (int r = 0; r < NR; ++r) ll_store(mg_vec(Q.xch[r], par, rank, NR, xlen) + n + q, pa, flag);
       if (tid == THREADS - 1)
-        for (int r = 0; r < NR; ++r) mg_vec(Q.xch[r], par, rank, NR, xlen)[n + 2 * NB] = yv;
+        for (int r = 0; r < NR; ++r) ll_store(mg_vec(Q.xch[r], par, rank, NR, xlen) + n + 2 * NB, yv, flag);
     }
     if (row_warp) {
       for (int base = j + 1; base < n; base += nslots) {  // trip count uniform within the warp (shuffles inside)
@@ -361,40 +388,20 @@ static __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel_mg(MgParams Q
         double acc = mg_row_partial(P, um, i, live, sub);
 #pragma unroll
         for (int o = 1; o < TPR; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (live && sub < NR) mg_vec(Q.xch[sub], par, rank, NR, xlen)[i] = acc;  // lane `sub` serves rank `sub`
+        if (live && sub < NR) ll_store(mg_vec(Q.xch[sub], par, rank, NR, xlen) + i, acc, flag);  // lane `sub` serves rank `sub`
       }
     }
-    // arrival: all stores of this CTA precede the release; every rank's counter gets one tick per CTA
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence_system();
-      for (int r = 0; r < NR; ++r)
-        asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(reinterpret_cast<unsigned*>(Q.xch[r])) : "memory");
-      const unsigned target = (unsigned)(j + 1) * (unsigned)NR * nblocks;
-      unsigned spins = 0, seen;
-      unsigned long long t_start = 0;
-      do {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr_local) : "memory");
-        if ((++spins & 0xffffu) == 0) {  // a lost peer must fault, not hang the device: 20 s of wall clock
-          unsigned long long now;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-          if (t_start == 0) t_start = now;
-          else if (now - t_start > 20000000000ull) __trap();
-        }
-      } while (seen < target);
-    }
-    __syncthreads();
 
     // ---------------- row phase: w, final W(:, jj), and the update of column j + 1 (replicated) ----------
     const bool more = jj + 1 < P.pw;
     if (tid < 2 * jj) {
       double s = 0;
-      for (int r = 0; r < NR; ++r) s += mg_vec(xloc, par, r, NR, xlen)[n + tid];
+      for (int r = 0; r < NR; ++r) s += ll_load(mg_vec(xloc, par, r, NR, xlen) + n + tid, flag);
       if (tid < jj) s_p1[tid] = s; else s_p2[tid - jj] = s;
     }
     if (tid == THREADS - 1) {
       double s = 0;
-      for (int r = 0; r < NR; ++r) s += mg_vec(xloc, par, r, NR, xlen)[n + 2 * NB];
+      for (int r = 0; r < NR; ++r) s += ll_load(mg_vec(xloc, par, r, NR, xlen) + n + 2 * NB, flag);
       s_yv = s;
     }
     int i = row_warp ? j + 1 + slot : j + 1;
@@ -410,7 +417,7 @@ static __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel_mg(MgParams Q
         vv[u] = on ? A[row + (long long)(P.j0 + t) * lda] : 0.0;
         ww[u] = on ? W[row + (long long)t * n] : 0.0;
       }
-      return (on_row && sub < NR) ? mg_vec(xloc, par, sub, NR, xlen)[row] : 0.0;  // one rank's share per lane
+      return (on_row && sub < NR) ? ll_load(mg_vec(xloc, par, sub, NR, xlen) + row, flag) : 0.0;  // one rank's share per lane
     };
     double acc = load_row(i, live);
     if (!row_warp && lane < TPR) {
@@ -468,11 +475,12 @@ static __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel_mg(MgParams Q
 }
 
 // One rank's side of the fused factorisation.  A: n x n column-major, replicated, lower triangle referenced.
-// xch[q]: exchange region of rank q as mapped here, mg_region_doubles(n, nranks) doubles, the first XCH_HDR
-// doubles of EVERY region zeroed and a barrier passed before any rank calls.  grid <= SM count CTAs.
+// xch[q]: exchange region of rank q as mapped here, mg_region_doubles(n, nranks) doubles.  epoch: 1 .. 65535, the same
+// on every rank and different from the epoch of the previous factorisation that used the regions (packet flags);
+// the regions are zeroed (and a barrier passed) whenever the epoch counter wraps.  n <= 65,535.  grid <= SM count CTAs.
 inline cudaError_t run_mg(cublasHandle_t blas, cudaStream_t stream, double* A, int64_t n, int64_t lda, double* d, double* e,
-                          double* tau, double* work, int nranks, int rank, double* const* xch, int grid, int64_t* launches,
-                          const Hooks* hooks = nullptr) {
+                          double* tau, double* work, int nranks, int rank, double* const* xch, unsigned epoch, int grid,
+                          int64_t* launches, const Hooks* hooks = nullptr) {
   if (n < 1) return cudaSuccess;
   const int64_t mB = (n + TILE - 1) / TILE;
   MgParams Q;
@@ -487,7 +495,7 @@ inline cudaError_t run_mg(cublasHandle_t blas, cudaStream_t stream, double* A, i
   if ((w - work) & 1) ++w;
   P.slots = reinterpret_cast<unsigned long long*>(w);
   P.prof = nullptr;
-  Q.nranks = nranks; Q.rank = rank; Q.xlen = mg_xlen(n);
+  Q.nranks = nranks; Q.rank = rank; Q.xlen = mg_xlen(n); Q.epoch = epoch;
   for (int q = 0; q < MG_MAX_RANKS; ++q) Q.xch[q] = q < nranks ? xch[q] : nullptr;
   cublasSetStream(blas, stream);
   {
