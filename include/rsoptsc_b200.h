@@ -216,7 +216,9 @@ int rsoptsc_debug_gemm(int32_t op, const double* A, const double* B, double* C, 
  * one of the two solvers behind the SVT of rsoptsc_computeM (R/SimilarityM.R:142-155):
  *   solver 0: cuSOLVER syevd;  solver 1: native (cooperative-kernel tridiagonalisation, tridiagonal
  *   divide and conquer with tcgen05 GEMMs, back-transformation);  solver 2: the native solver as a
- *   collective over the ranks of the active communicator (every rank passes the same matrix).
+ *   collective over the ranks of the active communicator (every rank passes the same matrix);
+ *   solver 3: eigenvalues only, the path of the PCA spectrum (a2) and the Laplacian spectrum (a14): own
+ *   tridiagonalisation + bisection on Sturm counts (V_out is not written).
  * lam_out (n) ascending eigenvalues, V_out (n x n, may be NULL) eigenvectors.  reps >= 1 repetitions
  * are timed with CUDA events; *ms_out (may be NULL) = mean ms per call. */
 int rsoptsc_debug_sym_eig(const double* A, int64_t n, int32_t solver, double* lam_out, double* V_out,
@@ -227,6 +229,9 @@ int rsoptsc_debug_sym_eig(const double* A, int64_t n, int32_t solver, double* la
  * run): d (k) diagonal in / ascending eigenvalues out, e (k-1) off-diagonal, V (k x k
  * column-major eigenvectors, may be NULL). */
 int rsoptsc_host_tridiag_eig(int32_t k, double* d, const double* e, double* V);
+/* Eigenvalues of the same tridiagonal by bisection on Sturm counts, with the arithmetic of the device
+ * kernel behind the values-only eigensolver (csrc/tridiag_bisect.h): lam (k) ascending. */
+int rsoptsc_host_tridiag_bisect(int32_t k, const double* d, const double* e, double* lam);
 /* The K rule of R/SimilarityM.R:61-72 applied to a descending PCA spectrum of length len. */
 int32_t rsoptsc_host_choose_K(const double* eig, int64_t len);
 /* Multi-GPU split of one computeM problem over nranks ranks (no GPU needed): for the neighbour table

@@ -7,6 +7,7 @@
 #include "comm.h"
 #include "gemm.h"
 #include "internal.h"
+#include "tridiag_bisect.h"
 
 namespace rs {
 
@@ -729,7 +730,7 @@ int rsoptsc_debug_sym_eig(const double* A, int64_t n, int32_t solver, double* la
                           double* ms_out) {
   return guarded([&] {
     cudaStream_t s = ctx().stream;
-    RS_REQUIRE(A && lam_out && n >= 1 && n <= 65535 && reps >= 1 && solver >= 0 && solver <= 2, "debug_sym_eig: bad arguments");
+    RS_REQUIRE(A && lam_out && n >= 1 && n <= 65535 && reps >= 1 && solver >= 0 && solver <= 3, "debug_sym_eig: bad arguments");
     const size_t nn = (size_t)n * n;
     DevBuf<double> a0(nn), a(nn), lam(n);
     a0.upload(A, nn, s);
@@ -740,6 +741,7 @@ int rsoptsc_debug_sym_eig(const double* A, int64_t n, int32_t solver, double* la
       RS_CUDA(cudaMemcpyAsync(a.p, a0.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, s));
       RS_CUDA(cudaEventRecord(e0, s));
       if (solver == 2) sym_eig(a.p, n, lam.p, true, -1.0e300, /*collective=*/true);  // all ranks of the communicator
+      else if (solver == 3) sym_eig(a.p, n, lam.p, /*vectors=*/false);              // values only (a2, a14)
       else sym_eig_select(a.p, n, lam.p, solver);
       RS_CUDA(cudaEventRecord(e1, s));
       RS_CUDA(cudaEventSynchronize(e1));
@@ -750,8 +752,26 @@ int rsoptsc_debug_sym_eig(const double* A, int64_t n, int32_t solver, double* la
     if (ms_out) *ms_out = total / reps;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     lam.download(lam_out, n, s);
-    if (V_out) a.download(V_out, nn, s);
+    if (V_out && solver != 3) a.download(V_out, nn, s);
     RS_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int rsoptsc_host_tridiag_bisect(int32_t k, const double* d, const double* e, double* lam) {
+  return guarded([&] {
+    RS_REQUIRE(k >= 1 && d && lam && (e || k == 1), "tridiag_bisect: bad arguments");
+    std::vector<double> e2(std::max(1, k - 1), 0.0);
+    double lo = INFINITY, hi = -INFINITY, em = 0.0;
+    for (int i = 0; i < k; ++i) {
+      const double el = i > 0 ? std::fabs(e[i - 1]) : 0.0, er = i + 1 < k ? std::fabs(e[i]) : 0.0;
+      lo = std::min(lo, d[i] - el - er);
+      hi = std::max(hi, d[i] + el + er);
+      if (i + 1 < k) { e2[i] = e[i] * e[i]; em = std::max(em, e2[i]); }
+    }
+    const double pivmin = DBL_MIN * std::max(1.0, em), tnorm = std::max(std::fabs(lo), std::fabs(hi));
+    lo -= 2.0 * tnorm * DBL_EPSILON * k + 2.0 * pivmin;
+    hi += 2.0 * tnorm * DBL_EPSILON * k + 2.0 * pivmin;
+    for (int i = 0; i < k; ++i) lam[i] = bisect::kth_eigenvalue(d, e2.data(), k, i, lo, hi, pivmin);
   });
 }
 

@@ -15,6 +15,7 @@
 #include "comm.h"
 #include "internal.h"
 #include "sytrd_kernel.cuh"
+#include "tridiag_bisect.h"
 
 namespace rs {
 
@@ -220,6 +221,64 @@ static void sym_eig_native(double* d_A, int64_t n, double* d_lam, double keep_ab
   }
 }
 
+// ---- values only: own tridiagonalisation + bisection on Sturm counts (tridiag_bisect.h), one thread per eigenvalue ---
+// scal: [0] gl, [1] gu (Gershgorin interval, widened as in dstebz), [2] pivmin
+__global__ void k_bisect_prep(const double* __restrict__ d, const double* __restrict__ e, int n, double* __restrict__ e2,
+                              double* __restrict__ scal) {
+  __shared__ double s_lo[32], s_hi[32], s_e[32];
+  double lo = INFINITY, hi = -INFINITY, em = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double el = i > 0 ? fabs(e[i - 1]) : 0.0, er = i + 1 < n ? fabs(e[i]) : 0.0;
+    lo = fmin(lo, d[i] - el - er);
+    hi = fmax(hi, d[i] + el + er);
+    if (i + 1 < n) { const double x = e[i] * e[i]; e2[i] = x; em = fmax(em, x); }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    em = fmax(em, __shfl_xor_sync(0xffffffffu, em, o));
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_lo[w] = lo; s_hi[w] = hi; s_e[w] = em; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (unsigned k = 1; k < blockDim.x / 32; ++k) { lo = fmin(lo, s_lo[k]); hi = fmax(hi, s_hi[k]); em = fmax(em, s_e[k]); }
+    const double pivmin = DBL_MIN * fmax(1.0, em);
+    const double tnorm = fmax(fabs(lo), fabs(hi));
+    scal[0] = lo - 2.0 * tnorm * DBL_EPSILON * n - 2.0 * pivmin;
+    scal[1] = hi + 2.0 * tnorm * DBL_EPSILON * n + 2.0 * pivmin;
+    scal[2] = pivmin;
+  }
+}
+__global__ void k_bisect(const double* __restrict__ d, const double* __restrict__ e2, int n, const double* __restrict__ scal,
+                         double* __restrict__ lam) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) lam[k] = bisect::kth_eigenvalue(d, e2, n, k, scal[0], scal[1], scal[2]);
+}
+void tridiag_eigenvalues_device(const double* d_d, const double* d_e, int64_t n, double* d_lam) {
+  DevBuf<double> e2(std::max<int64_t>(n, 1)), scal(4);
+  RS_LAUNCH(k_bisect_prep, 1, 1024, 0, d_d, d_e, (int)n, e2.p, scal.p);
+  RS_LAUNCH(k_bisect, (unsigned)cdiv(n, 64), 64, 0, d_d, e2.p, (int)n, scal.p, d_lam);  // 64 threads/CTA: spread over the SMs
+}
+
+static void sym_eigvals_native(double* d_A, int64_t n, double* d_lam) {
+  Context& c = ctx();
+  if (n == 1) {
+    RS_CUDA(cudaMemcpyAsync(d_lam, d_A, sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+    return;
+  }
+  DevBuf<double> d(n), e(n), tau(n);
+  {
+    Phase ph("eig_sytrd");
+    DevBuf<double> work(sytrd::workspace_doubles(n));
+    int64_t launches = 0;
+    RS_CUDA(sytrd::run(c.cublas, c.stream, d_A, n, n, d.p, e.p, tau.p, work.p, &launches));
+    g_launches.fetch_add(launches, std::memory_order_relaxed);
+  }
+  Phase ph("eig_bisect");
+  tridiag_eigenvalues_device(d.p, e.p, n, d_lam);
+}
+
 static void sym_eig_library(double* d_A, int64_t n, double* d_lam, bool vectors);
 
 void sym_eig_select(double* d_A, int64_t n, double* d_lam, int solver) {
@@ -234,6 +293,8 @@ void sym_eig(double* d_A, int64_t n, double* d_lam, bool vectors, double keep_ab
   // collective calls always take the native solver: its stages are the ones that are split across the ranks
   if (vectors && n <= 65535 && ((collective && sharded() && n >= 2) || (native_min_n() >= 0 && n >= native_min_n())))
     return sym_eig_native(d_A, n, d_lam, keep_above, collective);
+  // spectra without vectors (PCA a2, Laplacian a14): own tridiagonalisation + bisection, any size up to 65,535
+  if (!vectors && native_min_n() >= 0 && n <= 65535) return sym_eigvals_native(d_A, n, d_lam);
   sym_eig_library(d_A, n, d_lam, vectors);
 }
 

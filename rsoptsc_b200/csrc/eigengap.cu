@@ -48,28 +48,15 @@ static void block_eigenvalues(double* d_L, int64_t nc, std::vector<double>& out)
   RS_CUDA(cudaStreamSynchronize(c.stream));
 }
 
-// Spectrum of I - D^-1/2 S D^-1/2.  The Laplacian is block diagonal over the connected components
-// of the non-zero pattern of S, so its spectrum is the union of the blocks' spectra (sum n_c^3
-// eigensolver work instead of n^3).  The pattern is taken from the CSC view when S is sparse.
-static void laplacian_spectrum(const double* d_S, int64_t n, std::vector<double>& vals, const Compressed* csc_in = nullptr) {
+// Connected components of the non-zero pattern (host union-find over the compressed entries); an effectively
+// dense matrix is one block.  members[c] = ascending cells of component c, components numbered by lowest cell.
+static void pattern_components(const Compressed& csc, int64_t n, std::vector<std::vector<int>>& members) {
   Context& c = ctx();
-  RS_REQUIRE(n <= 65535, "get_components: n too large for this launch shape");
-  DevBuf<double> ones(n), deg(n);
-  RS_LAUNCH(k_fill_ones, (unsigned)cdiv(n, ET), ET, 0, ones.p, n);
-  DenseMatvec mv;
-  mv.init(d_S, n, n);
-  mv.mul_n(ones.p, deg.p);                                   // degree = S 1      (R :98)
-  RS_LAUNCH(k_inv_sqrt, (unsigned)cdiv(n, ET), ET, 0, deg.p, n);
-  // connected components of the pattern (host union-find over the sparse entries)
-  Compressed own;
-  const Compressed* csc = csc_in;
-  if (!csc) { compress(d_S, n, false, own); csc = &own; }
-  std::vector<int> comp(n, 0);
-  std::vector<std::vector<int>> members;
-  if (csc->nnz <= 128 * n) {
-    std::vector<int> ptr(n + 1), idx(std::max<int64_t>(csc->nnz, 1)), parent(n);
-    csc->ptr.download(ptr.data(), n + 1, c.stream);
-    if (csc->nnz) csc->idx.download(idx.data(), csc->nnz, c.stream);
+  members.clear();
+  if (csc.nnz <= 128 * n) {
+    std::vector<int> ptr(n + 1), idx(std::max<int64_t>(csc.nnz, 1)), parent(n);
+    csc.ptr.download(ptr.data(), n + 1, c.stream);
+    if (csc.nnz) csc.idx.download(idx.data(), csc.nnz, c.stream);
     RS_CUDA(cudaStreamSynchronize(c.stream));
     for (int64_t i = 0; i < n; ++i) parent[i] = (int)i;
     auto find = [&](int x) {
@@ -91,6 +78,25 @@ static void laplacian_spectrum(const double* d_S, int64_t n, std::vector<double>
     members.emplace_back(n);
     for (int64_t i = 0; i < n; ++i) members[0][i] = (int)i;
   }
+}
+
+// Spectrum of I - D^-1/2 S D^-1/2.  The Laplacian is block diagonal over the connected components
+// of the non-zero pattern of S, so its spectrum is the union of the blocks' spectra (sum n_c^3
+// eigensolver work instead of n^3).  The pattern is taken from the CSC view when S is sparse.
+static void laplacian_spectrum(const double* d_S, int64_t n, std::vector<double>& vals, const Compressed* csc_in = nullptr) {
+  Context& c = ctx();
+  RS_REQUIRE(n <= 65535, "get_components: n too large for this launch shape");
+  DevBuf<double> ones(n), deg(n);
+  RS_LAUNCH(k_fill_ones, (unsigned)cdiv(n, ET), ET, 0, ones.p, n);
+  DenseMatvec mv;
+  mv.init(d_S, n, n);
+  mv.mul_n(ones.p, deg.p);                                   // degree = S 1      (R :98)
+  RS_LAUNCH(k_inv_sqrt, (unsigned)cdiv(n, ET), ET, 0, deg.p, n);
+  Compressed own;
+  const Compressed* csc = csc_in;
+  if (!csc) { compress(d_S, n, false, own); csc = &own; }
+  std::vector<std::vector<int>> members;
+  pattern_components(*csc, n, members);
   vals.clear();
   vals.reserve(n);
   DevBuf<int> d_mem(n);
@@ -172,6 +178,195 @@ static bool pca_scores_sparse(const Compressed& csr, const Compressed& csc, int6
   for (int i = 0; i < ncomp; ++i) tc_mul(V.p + (size_t)i * n, d_scores + (size_t)i * n);
   RS_CUDA(cudaStreamSynchronize(ctx().stream));
   return true;
+}
+
+// ---- a14 without the spectrum: how many eigenvalues of Lsym are <= tol ------------------------------------
+// CountClusters only needs n_eigs of the similarity's Laplacian (R/Clustering.R:63); eigen(only.values) of an
+// n x n matrix is O(n^3) for a number that lives at the low end of the spectrum.  Lsym <= tol  <=>  the scaled
+// similarity M = D^-1/2 S D^-1/2 has an eigenvalue >= 1 - tol, so per connected component (inside one the
+// eigenvalue 1 of M is simple) a Lanczos process with full reorthogonalisation on the sparse M finds the top of the
+// spectrum; a second, deflated run certifies that no copy of a multiple eigenvalue was missed.  Components
+// too small to bother (or a run that cannot be certified) go through the dense values-only eigensolver.
+__global__ void k_scale_by(double* __restrict__ y, const double* __restrict__ x, const double* __restrict__ dd, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * ET + threadIdx.x;
+  if (i < n) y[i] = x[i] * dd[i];
+}
+__global__ void k_axpy_dev(double* __restrict__ w, const double* __restrict__ y, int64_t n, const double* __restrict__ s) {
+  const int64_t i = (int64_t)blockIdx.x * ET + threadIdx.x;
+  if (i < n) w[i] -= y[i] * (*s);
+}
+
+// eigenvalues >= T of M restricted to the component `mem`; returns -1 when the count could not be certified
+static int lanczos_count_top(const Compressed& csr, const double* dd, int64_t n, const std::vector<int>& mem, double T) {
+  Phase ph("lanczos_count");
+  cudaStream_t st = ctx().stream;
+  const unsigned g = (unsigned)cdiv(n, ET);
+  const int64_t nc = (int64_t)mem.size();
+  DevBuf<double> t(n), start(n), scal(2);
+  std::vector<double> Yh;        // converged eigenvectors (host bookkeeping of the count only)
+  DevBuf<double> Y;              // n x found
+  int found = 0;
+  const int max_steps = (int)std::min<int64_t>(nc, 640);
+  for (int round = 0; round < 6; ++round) {
+    // start vector: deterministic pseudo-random values on the component, zero elsewhere (the operator keeps
+    // that support exactly), orthogonalised against the eigenvectors found so far
+    std::vector<double> h(n, 0.0);
+    uint32_t x = 0x9e3779b9u * (uint32_t)(round + 1);
+    for (int i : mem) {
+      x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+      h[i] = 0.25 + (double)(x & 0xffffff) / 16777216.0;
+    }
+    start.upload(h.data(), n, st);
+    auto deflate = [&](double* w) {
+      for (int c = 0; c < found; ++c) {
+        RS_LAUNCH(k_dot1, 1, 1024, 0, Y.p + (size_t)c * n, w, n, scal.p);
+        RS_LAUNCH(k_axpy_dev, g, ET, 0, w, Y.p + (size_t)c * n, n, scal.p);
+      }
+    };
+    deflate(start.p);
+    RS_CUDA(cudaStreamSynchronize(st));  // `h` is read by the upload until here
+    Lanczos lz;
+    lz.init(n, max_steps, [&](const double* v, double* w) {
+      RS_LAUNCH(k_scale_by, g, ET, 0, t.p, v, dd, n);
+      spmv(csr, t.p, w);
+      RS_LAUNCH(k_scale_by, g, ET, 0, w, w, dd, n);
+      deflate(w);
+    }, start.p);
+    std::vector<double> theta, S;
+    bool done = false;
+    std::vector<int> top;  // converged Ritz values >= T of this round
+    while (!done) {
+      lz.advance(lz.steps == 0 ? 48 : 24);
+      if (lz.nonfinite) return -1;
+      const int k = lz.steps;
+      if (k == 0) { done = true; break; }  // start vector vanished under deflation: nothing left in this component
+      lz.ritz(theta, S, /*last_row_only=*/true);
+      const double bk = lz.exhausted ? 0.0 : std::fabs(lz.beta[k - 1]);
+      // all Ritz values that could be >= T must have converged, and the first one below T must be a converged
+      // (hence genuine) eigenvalue approximation: the top of the spectrum is then complete
+      bool ok = true, below = lz.exhausted;
+      top.clear();
+      for (int i = k - 1; i >= 0; --i) {
+        const double r = bk * std::fabs(S[i]);
+        if (theta[i] + r >= T) {
+          if (r > 1e-10) { ok = false; break; }
+          if (theta[i] >= T) top.push_back(i);
+        } else {
+          below = below || r <= 1e-6;
+          break;
+        }
+      }
+      if (ok && (below || (int)top.size() == k)) done = true;
+      else if (k >= lz.max_steps) return -1;
+    }
+    if (top.empty()) return found;        // certified: the deflated operator has nothing left above T
+    // keep the Ritz vectors of the new eigenvalues for the deflation of the next round
+    lz.ritz(theta, S);
+    DevBuf<double> Ynew((size_t)n * (found + top.size()));
+    if (found) RS_CUDA(cudaMemcpyAsync(Ynew.p, Y.p, sizeof(double) * (size_t)n * found, cudaMemcpyDeviceToDevice, st));
+    lz.ritz_vectors(S, top, Ynew.p + (size_t)n * found);
+    Y = std::move(Ynew);
+    found += (int)top.size();
+    if ((int64_t)found >= nc) return found;
+  }
+  return -1;
+}
+
+// #{eigenvalues of Lsym(S) <= tol} for a sparse similarity (CSR + CSC views given)
+static int laplacian_count_le(const double* d_S, int64_t n, double tol, const Compressed& csr, const Compressed& csc) {
+  Context& c = ctx();
+  DevBuf<double> ones(n), dd(n);
+  RS_LAUNCH(k_fill_ones, (unsigned)cdiv(n, ET), ET, 0, ones.p, n);
+  spmv(csr, ones.p, dd.p);                                   // degree = S 1      (R :98)
+  RS_LAUNCH(k_inv_sqrt, (unsigned)cdiv(n, ET), ET, 0, dd.p, n);
+  std::vector<std::vector<int>> members;
+  pattern_components(csc, n, members);
+  int count = 0;
+  DevBuf<int> d_mem(n);
+  for (const auto& mem : members) {
+    const int64_t nc = (int64_t)mem.size();
+    int got = -1;
+    if (nc >= 1024) got = lanczos_count_top(csr, dd.p, n, mem, 1.0 - tol);
+    if (got < 0) {  // small block, or not certified: all eigenvalues of the dense block
+      if (nc >= 1024) add_counter("laplacian_count_dense_fallback", 1.0);
+      DevBuf<double> L((size_t)nc * nc);
+      d_mem.upload(mem.data(), nc, c.stream);
+      dim3 grid((unsigned)std::min<int64_t>(cdiv(nc, ET), 64), (unsigned)nc);
+      RS_LAUNCH(k_laplacian_block, grid, ET, 0, d_S, dd.p, n, d_mem.p, nc, L.p);
+      RS_CUDA(cudaStreamSynchronize(c.stream));
+      std::vector<double> v;
+      block_eigenvalues(L.p, nc, v);
+      got = 0;
+      for (double x : v) got += std::fabs(x) <= tol;
+    }
+    count += got;
+  }
+  return count;
+}
+
+// ---- a14 on the consensus matrix: exact spectrum through the label signatures ------------------------------
+// consen[i,j] depends only on the label signatures (columns of the R x n table) of i and j, so with the G distinct
+// signatures, their multiplicities s_g and the G x G matrix C^ between them, D^-1/2 C D^-1/2 = P M^ P^T
+// (P: n x G membership, M^_gh = C^_gh / sqrt(delta_g delta_h), delta = C^ s).  Its non-zero eigenvalues are those of
+// the G x G matrix sqrt(s_g s_h) M^_gh; the other n - G are zero.  Hence the spectrum of Lsym is
+// {1 - mu_g} u {1 (n - G times)}: an O(n R log n + G^3) computation instead of a dense n x n eigensolve, and the
+// n x n consensus matrix is never formed (R/Clustering.R:72, 96-105, 143-153).
+__global__ void k_scale_sym(double* __restrict__ B, const double* __restrict__ w, int64_t G) {
+  const int64_t h = blockIdx.y;
+  for (int64_t g = (int64_t)blockIdx.x * ET + threadIdx.x; g < G; g += (int64_t)gridDim.x * ET) B[g + h * G] *= w[g] * w[h];
+}
+static void consensus_laplacian_spectrum(const std::vector<int32_t>& table, int R, int64_t n, double tau,
+                                         std::vector<double>& vals) {
+  Phase ph("consensus_spectrum");
+  cudaStream_t st = ctx().stream;
+  // group the cells by signature (lexicographic sort of the n columns)
+  std::vector<int> order(n);
+  for (int64_t i = 0; i < n; ++i) order[i] = (int)i;
+  auto less = [&](int a, int b) {
+    for (int r = 0; r < R; ++r) {
+      const int32_t x = table[(size_t)r * n + a], y = table[(size_t)r * n + b];
+      if (x != y) return x < y;
+    }
+    return false;
+  };
+  std::sort(order.begin(), order.end(), less);
+  std::vector<int> rep;
+  std::vector<double> size;
+  for (int64_t i = 0; i < n; ++i) {
+    if (i == 0 || less(order[i - 1], order[i])) { rep.push_back(order[i]); size.push_back(0.0); }
+    size.back() += 1.0;
+  }
+  const int64_t G = (int64_t)rep.size();
+  add_counter("consensus_signatures", (double)G);
+  std::vector<int32_t> sub((size_t)R * G);
+  for (int r = 0; r < R; ++r)
+    for (int64_t g = 0; g < G; ++g) sub[(size_t)r * G + g] = table[(size_t)r * n + rep[g]];
+  DevBuf<int32_t> d_sub(sub.size());
+  d_sub.upload(sub.data(), sub.size(), st);
+  DevBuf<double> B((size_t)G * G), s(G), delta(G), lam(G);
+  consensus_dense(d_sub.p, R, G, tau, B.p);                  // C^ (symmetric, thresholded)
+  s.upload(size.data(), G, st);
+  DenseMatvec mv;
+  mv.init(B.p, G, G);
+  mv.mul_n(s.p, delta.p);                                    // degree of any cell of group g
+  std::vector<double> hd(G), w(G);
+  delta.download(hd.data(), G, st);
+  RS_CUDA(cudaStreamSynchronize(st));
+  for (int64_t g = 0; g < G; ++g) w[g] = std::sqrt(size[g] / hd[g]);
+  s.upload(w.data(), G, st);
+  dim3 grid((unsigned)std::min<int64_t>(cdiv(G, ET), 64), (unsigned)G);
+  RS_LAUNCH(k_scale_sym, grid, ET, 0, B.p, s.p, G);
+  RS_CUDA(cudaStreamSynchronize(st));
+  {
+    Phase pe("eig");
+    sym_eig(B.p, G, lam.p, /*vectors=*/false);
+  }
+  std::vector<double> mu(G);
+  lam.download(mu.data(), G, st);
+  RS_CUDA(cudaStreamSynchronize(st));
+  vals.assign(n, 1.0);                                       // the n - G exchangeable directions
+  for (int64_t g = 0; g < G; ++g) vals[g] = std::fabs(1.0 - mu[g]);   // abs(Re(.))   (R :102)
+  std::sort(vals.begin(), vals.end());                       // sort         (R :104)
 }
 
 void get_components(const double* d_S, int64_t n, double tol, double* h_vals, int32_t* n_eigs) {
@@ -538,9 +733,14 @@ void count_clusters(const double* d_S, int64_t n, double tol, int lo, int hi, in
   Compressed csr, csc;
   compress(d_S, n, true, csr);
   compress(d_S, n, false, csc);
-  laplacian_spectrum(d_S, n, vals, &csc);                                 // R :63
+  // R :63 -- only n_eigs of the similarity's Laplacian is used: Lanczos count on the sparse similarity
   int solo = 0;
-  for (double v : vals) solo += v <= tol;
+  if (csr.nnz <= 128 * n && !getenv("RSOPTSC_EIGENGAP_DENSE")) {
+    solo = laplacian_count_le(d_S, n, tol, csr, csc);
+  } else {
+    laplacian_spectrum(d_S, n, vals, &csc);
+    for (double v : vals) solo += v <= tol;
+  }
   const double tau = solo <= 5 ? 0.3 : (solo <= 10 ? 0.4 : 0.5);          // R :64-70
   // GetEnsemble (R :125-154): PCA scores of t(S), PAM for every k in range, consensus
   DevBuf<double> scores((size_t)n * n_comp);
@@ -561,11 +761,15 @@ void count_clusters(const double* d_S, int64_t n, double tol, int lo, int hi, in
       std::copy(lab.begin(), lab.end(), table.begin() + (size_t)(k - lo) * n);
     }
   }
-  DevBuf<int32_t> d_table(table.size());
-  d_table.upload(table.data(), table.size(), st);
-  DevBuf<double> consen((size_t)n * n);
-  consensus_dense(d_table.p, R, n, tau, consen.p);                        // R :143-153
-  laplacian_spectrum(consen.p, n, vals);                                  // R :72
+  if (getenv("RSOPTSC_EIGENGAP_DENSE")) {                                 // the literal route (tests compare the two)
+    DevBuf<int32_t> d_table(table.size());
+    d_table.upload(table.data(), table.size(), st);
+    DevBuf<double> consen((size_t)n * n);
+    consensus_dense(d_table.p, R, n, tau, consen.p);                      // R :143-153
+    laplacian_spectrum(consen.p, n, vals);                                // R :72
+  } else {
+    consensus_laplacian_spectrum(table, R, n, tau, vals);                 // R :143-153 + :72, by label signature
+  }
   double best = -INFINITY;
   int arg = 0;
   for (int64_t i = 0; i + 1 < n; ++i) {                                   // R :74-75 (first maximum)

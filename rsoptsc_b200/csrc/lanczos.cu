@@ -247,7 +247,7 @@ void DenseMatvec::mul_n(const double* x, double* y) {  // y(rows) = M x(cols)
 }
 
 // ---- Lanczos engine ---------------------------------------------------------------------
-void Lanczos::init(int64_t dim_, int max_steps_, std::function<void(const double*, double*)> op_) {
+void Lanczos::init(int64_t dim_, int max_steps_, std::function<void(const double*, double*)> op_, const double* d_start) {
   dim = dim_;
   max_steps = (int)std::min<int64_t>(max_steps_, dim_);
   op = std::move(op_);
@@ -259,7 +259,8 @@ void Lanczos::init(int64_t dim_, int max_steps_, std::function<void(const double
   partial.alloc(LB);
   steps = 0;
   alpha.clear(); beta.clear();
-  RS_LAUNCH(k_start_vector, LB, LT, 0, Q.p, dim);
+  if (d_start) RS_CUDA(cudaMemcpyAsync(Q.p, d_start, sizeof(double) * dim, cudaMemcpyDeviceToDevice, ctx().stream));
+  else RS_LAUNCH(k_start_vector, LB, LT, 0, Q.p, dim);
   RS_LAUNCH(k_dot_partial, LB, LT, 0, Q.p, Q.p, dim, partial.p);
   RS_LAUNCH(k_scale_by_norm, LB, LT, 0, Q.p, dim, partial.p, LB, (double*)nullptr);
 }

@@ -25,7 +25,8 @@ struct Lanczos {  // symmetric Lanczos with full reorthogonalisation on a device
   std::function<void(const double*, double*)> op;  // w = B v (device pointers)
   DevBuf<double> Q, w, coef, d_alpha, d_beta, partial;
   std::vector<double> alpha, beta;
-  void init(int64_t dim, int max_steps, std::function<void(const double*, double*)> op);
+  // d_start (optional, dim values on the device): start vector instead of the built-in pseudo-random one
+  void init(int64_t dim, int max_steps, std::function<void(const double*, double*)> op, const double* d_start = nullptr);
   void advance(int more);
   // eigen-decomposition of the current tridiagonal: theta ascending, S steps x steps column-major
   void ritz(std::vector<double>& theta, std::vector<double>& S, bool last_row_only = false) const;

@@ -93,3 +93,28 @@ def test_host_choose_K_matches_oracle(lib):
         L = int(rng.integers(5, 400))
         eig = np.sort(rng.gamma(0.5, size=L))[::-1].copy()
         assert lib.rsoptsc_host_choose_K(eig.ctypes.data_as(_lib.c_double_p), L) == O.choose_K(eig)
+
+
+def test_host_tridiag_bisect(lib):
+    """The Sturm-count bisection behind the values-only eigensolver (csrc/tridiag_bisect.h, shared with the device
+    kernel): random, decoupled (zero off-diagonals), clustered and graded tridiagonals vs LAPACK."""
+    from scipy.linalg import eigvalsh_tridiagonal
+    rng = np.random.default_rng(0)
+    dp = _lib.c_double_p
+    for k in (1, 2, 3, 17, 200, 1000):
+        for kind in range(4):
+            d = rng.standard_normal(k)
+            e = rng.standard_normal(max(k - 1, 1))
+            if kind == 1:
+                e[::3] = 0
+            elif kind == 2:
+                d[:] = 1.0
+                e[:] = 1e-9
+            elif kind == 3:
+                d = np.linspace(-k, k, k) ** 3
+                e = np.ones(max(k - 1, 1))
+            lam = np.zeros(k)
+            assert lib.rsoptsc_host_tridiag_bisect(k, d.ctypes.data_as(dp), e.ctypes.data_as(dp), lam.ctypes.data_as(dp)) == 0
+            ref = eigvalsh_tridiagonal(d, e[:k - 1]) if k > 1 else d.copy()
+            assert np.all(np.diff(lam) >= 0)
+            assert np.abs(lam - ref).max() <= 5e-14 * max(np.abs(ref).max(), 1e-300), (k, kind)

@@ -574,3 +574,126 @@ def test_computeM_with_native_eigensolver():
     env = dict(os.environ, RSOPTSC_EIG="native", RSOPTSC_BACKTRANSFORM="native")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "native eig path ok" in r.stdout, r.stdout + r.stderr
+
+
+# ---- values-only eigensolver (a2, a14): own tridiagonalisation + bisection on Sturm counts -----------
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 31, 64, 65, 130, 700, 2300])
+def test_values_only_eigensolver(n):
+    rng = np.random.default_rng(100 + n)
+    if n % 2:
+        A = rng.standard_normal((n, n))
+        G = (A + A.T) / 2
+    else:  # Laplacian-like: eigenvalues in [0, 2] with a cluster at 1
+        B = rng.random((n, max(n // 3, 1)))
+        S = B @ B.T
+        dd = 1.0 / np.sqrt(S.sum(axis=1))
+        G = np.eye(n) - dd[:, None] * S * dd[None, :]
+    lam, _ = _sym_eig(G, 3)
+    ref = np.linalg.eigvalsh(G)
+    assert np.all(np.diff(lam) >= 0)
+    assert np.abs(lam - ref).max() <= 1e-13 * max(n, 8) * max(np.abs(ref).max(), 1e-300)
+
+
+def _count_clusters_both_routes(S, n_comp=3):
+    """CountClusters through the Lanczos count + signature-compressed consensus spectrum (default) and through the
+    literal dense route (RSOPTSC_EIGENGAP_DENSE=1: every spectrum from a dense values-only eigensolve)."""
+    import os
+    new = api.CountClusters(S, n_comp=n_comp)
+    os.environ["RSOPTSC_EIGENGAP_DENSE"] = "1"
+    try:
+        dense = api.CountClusters(S, n_comp=n_comp)
+    finally:
+        del os.environ["RSOPTSC_EIGENGAP_DENSE"]
+    return new, dense
+
+
+@pytest.mark.gpu
+def test_count_clusters_lanczos_route_equals_dense_route_fixture(joost):
+    new, dense = _count_clusters_both_routes(joost["S"])
+    assert new["upper_bound"] == dense["upper_bound"] == 9
+    assert new["lower_bound"] == dense["lower_bound"]
+    assert np.allclose(new["eigs"]["val"], dense["eigs"]["val"], atol=1e-10)
+
+
+@pytest.mark.gpu
+def test_count_clusters_lanczos_route_large_component():
+    """A similarity whose support has one component of > 1,024 cells: the n_eigs pre-estimate (R/Clustering.R:63)
+    comes from the certified Lanczos count on the sparse scaled similarity, the consensus spectrum from the
+    label signatures; both must reproduce the dense route."""
+    g = _golden_scale("cut3000")
+    n = int(g["cells"])
+    W = _W_from_support(g["idx"], g["Zs"], n)
+    api.timers(True)
+    new, dense = _count_clusters_both_routes(W)
+    rep = api.phase_report()
+    api.timers(False)
+    assert rep.get("lanczos_count", {}).get("calls", 0) > 0 and rep.get("consensus_spectrum", {}).get("calls", 0) > 0
+    assert new["upper_bound"] == dense["upper_bound"]
+    assert new["lower_bound"] == dense["lower_bound"]
+    assert np.allclose(new["eigs"]["val"], dense["eigs"]["val"], atol=1e-10)
+    # and the oracle's own GetComponents count on the same similarity
+    assert api.GetComponents(W)["n_eigs"] == O.GetComponents(W)["n_eigs"]
+
+
+# ---- parity at scale: golden vectors of the CPU oracle (tests/golden/make_golden_scale.py) -------------
+def _golden_scale(name):
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scale_%s.npz" % name)
+    if not os.path.exists(path):
+        pytest.skip("golden fixture %s not generated" % name)
+    return np.load(path)
+
+
+def _W_from_support(idx, Zs, n):
+    Z = np.zeros((n, n))
+    Z[np.arange(n)[:, None], idx] = Zs
+    Z[Z <= 2.220446049250313e-16] = 0
+    return (np.abs(Z) + np.abs(Z.T)) / 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["cut3000", "big6200"])
+def test_similarity_matches_oracle_golden_at_scale(case):
+    """Default path, no environment overrides (tcgen05 GEMMs; the 6,200-cell case has one connected block above
+    4,000 rows, so its SVTs go through the native eigensolver): Z on its support within 1e-6 relative
+    Frobenius of the oracle, same iteration count and stop reason, Err1 trace, K, neighbour table, labels."""
+    from rsoptsc_b200.synthetic import synthetic_lognorm
+    g = _golden_scale(case)
+    n = int(g["cells"])
+    data, _ = synthetic_lognorm(int(g["genes"]), int(g["gen_cells"]), seed=int(g["seed"]))
+    data = np.asfortranarray(data[:, :n])
+    api.timers(True)
+    r = api.SimilarityM(float(g["lam"]), data)
+    rep = api.phase_report()
+    api.timers(False)
+    assert r["K"] == int(g["K"])
+    assert r["iters"] == int(g["iters"])
+    assert abs(r["E"] - float(g["E"])) <= 1e-9 * float(g["E"])
+    idx = g["idx"]
+    Wref = _W_from_support(idx, g["Zs"], n)
+    assert relF(r["W"], Wref) < 1e-6
+    assert np.count_nonzero(r["W"]) == int(g["W_nnz"])
+    assert rep.get("ozaki_gemm", {}).get("calls", 0) > 0
+    if int(g["components"][0]) >= 4000:
+        assert rep.get("sytrd_panel", {}).get("calls", 0) > 0      # native eigensolver on the default path
+    c = api.ClusterCells(r["W"], n_clusters=int(g["rank"]))
+    assert c["iters"] == int(g["nmf_iters"])
+    assert np.array_equal(np.asarray(c["labels"]), g["labels"])
+
+
+@pytest.mark.gpu
+def test_computeM_err_trace_matches_oracle_golden():
+    """computeM on the oracle's own neighbour table: the per-iteration Err1 = ||XXZ - E||_2 trace
+    (R/SimilarityM.R:189) that drives the stop rule, and Z on the support."""
+    from rsoptsc_b200.synthetic import synthetic_lognorm
+    g = _golden_scale("cut3000")
+    n = int(g["cells"])
+    data, _ = synthetic_lognorm(int(g["genes"]), int(g["gen_cells"]), seed=int(g["seed"]))
+    X = api.normalize(np.asfortranarray(data[:, :n]))
+    r = api.computeM(None, X, float(g["lam"]), idx=g["idx"])
+    assert r["iters"] == int(g["iters"])
+    k = len(g["err1"])
+    assert np.allclose(r["Err"][:k, 0], g["err1"], rtol=1e-8, atol=1e-12)
+    Zs = r["Z"][np.arange(n)[:, None], g["idx"]]
+    assert relF(Zs, g["Zs"]) < 1e-6

@@ -91,3 +91,17 @@ def test_choose_K_bounds():
     assert O.choose_K(np.array([5.0, 1.0] + [1e-3] * 50)) == 10
     flat = np.ones(400)
     assert O.choose_K(flat) == 30
+
+
+def test_literal_and_restructured_oracle_agree():
+    """literal=True mirrors R line by line (full-SVD spectral norms every iteration, SVT before the stop test,
+    R/SimilarityM.R:142-163); literal=False is the restructured order every parity assertion uses (norms by
+    eigvalsh of the small Gram, stop test hoisted).  Same Z, E, iteration count and stop reason."""
+    from conftest import small_problem
+    p = small_problem(200, 300, seed=4)
+    forb = O.mask_from_idx(p["idx"], 300)
+    a = O.computeM(forb, p["X"], 0.5, literal=True)
+    b = O.computeM(forb, p["X"], 0.5, literal=False)
+    assert a["iters"] == b["iters"] and a["stop"] == b["stop"]
+    assert abs(a["E"] - b["E"]) <= 1e-10 * abs(a["E"])
+    assert np.linalg.norm(a["Z"] - b["Z"]) <= 1e-9 * np.linalg.norm(a["Z"])
