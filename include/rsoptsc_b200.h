@@ -23,12 +23,15 @@
 extern "C" {
 #endif
 
-#define RSOPTSC_ABI_VERSION 2
+#define RSOPTSC_ABI_VERSION 3
 
 /* stop codes of the ADMM (R/SimilarityM.R:134-137, :157-162, :191-194) */
 #define RSOPTSC_STOP_MAXITER 1
 #define RSOPTSC_STOP_ERRMIN 2
 #define RSOPTSC_STOP_EPSILON 3
+
+/* status returned when the caller's progress callback asked to stop (rsoptsc_set_progress) */
+#define RSOPTSC_STATUS_INTERRUPTED 7
 
 /* ---- lifecycle ------------------------------------------------------------------- */
 int rsoptsc_abi_version(void);
@@ -56,6 +59,19 @@ double rsoptsc_counter(const char* name);
 const char* rsoptsc_phase_name(int32_t i);
 int rsoptsc_timer_begin(const char* name);
 int rsoptsc_timer_end(const char* name);
+
+/* Progress / interrupt hook.  The reference prints `Err = ...` once per ADMM iteration
+ * (R/SimilarityM.R:191) and, being R code, can be interrupted between iterations; NMF::nmf checks its
+ * stop rule every 10 iterations (R/Clustering.R:29-33).  fn is called on the calling thread
+ *   stage RSOPTSC_STAGE_ADMM  once per computeM iteration, iter = the reference's `iter`, value = Err[iter, 1]
+ *   stage RSOPTSC_STAGE_NMF   at every connectivity check of the NMF, iter = iterations done, value = 0
+ * A non-zero return aborts the running entry point with RSOPTSC_STATUS_INTERRUPTED after the library has
+ * released its device memory (the R shim maps this to R_CheckUserInterrupt + Rprintf).  With a multi-GPU
+ * communicator every rank must return the same value.  fn = NULL removes the hook. */
+#define RSOPTSC_STAGE_ADMM 0
+#define RSOPTSC_STAGE_NMF 1
+typedef int (*rsoptsc_progress_fn)(int32_t stage, int32_t iter, double value, void* user);
+int rsoptsc_set_progress(rsoptsc_progress_fn fn, void* user);
 
 /* ---- multi-GPU: one process per GPU, one communicator per process ------
  * After rsoptsc_comm_init with nranks > 1 the library is SPMD: every rank calls the same entry point
@@ -135,6 +151,13 @@ int rsoptsc_similarity_dev(const double* d_data, int64_t m, int64_t n, const dou
                            int32_t emb_dim, double lambda, int32_t K_override, double* d_W,
                            double* E, int32_t* iters, int32_t* K_out);
 
+/* SimilarityM with a caller-supplied neighbour table: the reference's `use_umap_indices = TRUE` branch
+ * (R/SimilarityM.R:85-87, IDX <- data.umap$knn$indexes) and any other externally computed kNN graph.
+ * idx: n x K row-major, 0-based; row j lists the columns of Z that row j may use (:90-92).  The PCA rule for K
+ * (:41-72) does not apply (the table fixes the support); everything else as rsoptsc_similarity.  W: n x n. */
+int rsoptsc_similarity_knn(const double* data, int64_t m, int64_t n, const int32_t* idx, int32_t K,
+                           double lambda, double* W, double* E, int32_t* iters);
+
 /* ---- ClusterCells stages ---------------------------------------------------------- */
 /* a12-a13  NMF::nmf(V, rank=k, method='lee', seed='nndsvd') + row-argmax labels
  * (R/Clustering.R:29-37).  V: n x n non-negative (dense).  basis: n x k, coef: k x n
@@ -152,6 +175,11 @@ int rsoptsc_get_components(const double* S, int64_t n, double tol, double* vals,
 /* a17  GetConsensus + truncation of GetEnsemble (R/Clustering.R:143-153, :164-175):
  * labels: R x n row-major int32; consen: n x n; entries <= R*tau zeroed, then symmetrised. */
 int rsoptsc_consensus(const int32_t* labels, int32_t R, int64_t n, double tau, double* consen);
+/* a15-a17  GetEnsemble(data, tol, n_comp, tau, range = lo:hi)  R/Clustering.R:125-154: PCA scores of the
+ * similarity S (n x n), cluster::pam for every k in the range, summed consensus, truncation at
+ * (hi - lo + 1) * tau, symmetrisation.  consen: n x n.  (`tol` is unused by the reference's body.) */
+int rsoptsc_get_ensemble(const double* S, int64_t n, int32_t n_comp, double tau, int32_t range_lo,
+                         int32_t range_hi, double* consen);
 /* a16  cluster::pam(P, k)$clustering (R/Clustering.R:137): P n x dim column-major;
  * labels n (1-based, numbered by first appearance), medoids k (0-based). */
 int rsoptsc_pam(const double* P, int64_t n, int32_t dim, int32_t k, int32_t* labels,
@@ -208,6 +236,8 @@ int32_t rsoptsc_get_gemm_backend(void);
  *   op 1: C (M x N) = A B,    A: M x K, B: K x N
  *   op 2: C (M x N) = A B^T,  A: M x K, B: N x K
  *   op 3: C (M x N) = A^T B,  A: K x M, B: K x N
+ *   op 4: C (M x M, in/out, lower triangle) -= A B^T + B A^T,  A, B: M x K -- the rank-2K trailing update of
+ *         the tridiagonalisation, applied 1 + reps times (warm-up included)
  * reps >= 1 repetitions are timed with CUDA events; *ms_out (may be NULL) = mean ms per call. */
 int rsoptsc_debug_gemm(int32_t op, const double* A, const double* B, double* C, int64_t M,
                        int64_t N, int64_t K, int32_t backend, int32_t reps, double* ms_out);

@@ -34,6 +34,9 @@ double Rf_asReal(SEXP x);
 int Rf_asInteger(SEXP x);
 void Rf_error(const char* fmt, ...);
 void R_CheckUserInterrupt(void);
+Rboolean R_ToplevelExec(void (*fun)(void*), void* data);
+void Rprintf(const char* fmt, ...);
+char* R_alloc(size_t n, int size);
 #define PROTECT(x) Rf_protect(x)
 #define UNPROTECT(n) Rf_unprotect(n)
 typedef void* (*DL_FUNC)(void);

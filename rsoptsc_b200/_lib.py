@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(_HERE, "librsoptsc_b200.so")
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
 c_int64_p = C.POINTER(C.c_int64)
+# int (*rsoptsc_progress_fn)(int32_t stage, int32_t iter, double value, void* user)
+PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_int32, C.c_int32, C.c_double, C.c_void_p)
 
 # name -> (restype, argtypes); mirrors include/rsoptsc_b200.h one to one
 SIGNATURES = {
@@ -52,12 +54,16 @@ SIGNATURES = {
                                      c_int32_p, c_double_p]),
     "rsoptsc_similarity_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_double,
                                          C.c_int32, C.c_void_p, c_double_p, c_int32_p, c_int32_p]),
+    "rsoptsc_similarity_knn": (C.c_int, [c_double_p, C.c_int64, C.c_int64, c_int32_p, C.c_int32, C.c_double, c_double_p,
+                                         c_double_p, c_int32_p]),
+    "rsoptsc_set_progress": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rsoptsc_nmf_lee": (C.c_int, [c_double_p, C.c_int64, C.c_int32, C.c_int32, c_double_p, c_double_p, c_int32_p,
                                   c_int32_p]),
     "rsoptsc_nmf_lee_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, c_double_p, c_double_p, c_int32_p,
                                       c_int32_p]),
     "rsoptsc_get_components": (C.c_int, [c_double_p, C.c_int64, C.c_double, c_double_p, c_int32_p]),
     "rsoptsc_consensus": (C.c_int, [c_int32_p, C.c_int32, C.c_int64, C.c_double, c_double_p]),
+    "rsoptsc_get_ensemble": (C.c_int, [c_double_p, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_int32, c_double_p]),
     "rsoptsc_pam": (C.c_int, [c_double_p, C.c_int64, C.c_int32, C.c_int32, c_int32_p, c_int32_p]),
     "rsoptsc_count_clusters": (C.c_int, [c_double_p, C.c_int64, C.c_double, C.c_int32, C.c_int32, C.c_int32,
                                          c_int32_p, c_int32_p, c_double_p, c_int32_p]),

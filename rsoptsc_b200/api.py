@@ -101,15 +101,45 @@ def threshold_symmetrise(Z):
     return W
 
 
-def SimilarityM(lam=0.5, data=None, embedding=None, K=None, dense=True, sparse=False, W_out=None):
+_progress_keepalive = None
+
+
+def set_progress(fn):
+    """Install (fn) or remove (None) the progress / interrupt hook of the C ABI (rsoptsc_set_progress).
+    fn(stage, iter, value) is called once per computeM iteration (stage 0, value = Err[iter, 1], the number
+    the reference prints at R/SimilarityM.R:191) and at every NMF stop check (stage 1); a true return value
+    aborts the running call with RsoptscError (status 7, the R shim's R_CheckUserInterrupt)."""
+    global _progress_keepalive
+    lib = _lib.init()
+    if fn is None:
+        _lib.check(lib.rsoptsc_set_progress(None, None))
+        _progress_keepalive = None
+        return
+    cb = _lib.PROGRESS_FN(lambda stage, it, value, user: 1 if fn(int(stage), int(it), float(value)) else 0)
+    _lib.check(lib.rsoptsc_set_progress(C.cast(cb, C.c_void_p), None))
+    _progress_keepalive = cb
+
+
+def SimilarityM(lam=0.5, data=None, embedding=None, K=None, dense=True, sparse=False, W_out=None, knn_indices=None):
     """SimilarityM(lambda, data, ...) of R/SimilarityM.R:27 -> dict(W, E, nl_embedding, ...).
 
     `embedding` is what Rtsne/umap produce in the reference (n x >= 3); None selects the
     deterministic in-library PCA embedding.  `K` forces the neighbour count (config 5).
-    `W_out` (optional, n x n float64 Fortran-ordered, e.g. pinned memory) receives W."""
+    `W_out` (optional, n x n float64 Fortran-ordered, e.g. pinned memory) receives W.
+    `knn_indices` (n x K, 0-based) is the reference's `use_umap_indices = TRUE` branch (R/SimilarityM.R:85-87):
+    the caller's neighbour table replaces the in-library kNN search."""
     lib = _lib.init()
     d = _f64(data)
     m, n = d.shape
+    if knn_indices is not None:
+        idx = np.ascontiguousarray(knn_indices, dtype=np.int32)
+        if idx.ndim != 2 or idx.shape[0] != n:
+            raise ValueError("knn_indices must be n x K")
+        W = W_out if W_out is not None else np.empty((n, n), dtype=np.float64, order="F")
+        E, iters = C.c_double(0), C.c_int32(0)
+        _lib.check(lib.rsoptsc_similarity_knn(_dp(d), m, n, _ip(idx), idx.shape[1], float(lam), _dp(W), C.byref(E),
+                                              C.byref(iters)))
+        return dict(W=W, E=float(E.value), nl_embedding=embedding, iters=int(iters.value), K=int(idx.shape[1]))
     emb = None if embedding is None else _f64(embedding)
     if W_out is not None:
         if W_out.shape != (n, n) or W_out.dtype != np.float64 or not W_out.flags.f_contiguous:
@@ -170,6 +200,21 @@ def GetConsensusEnsemble(labels, tau):
     R, n = lab.shape
     out = np.empty((n, n), dtype=np.float64, order="F")
     _lib.check(lib.rsoptsc_consensus(_ip(lab), R, n, float(tau), _dp(out)))
+    return out
+
+
+def GetConsensus(clusters):
+    """GetConsensus(clusters) of R/Clustering.R:164-175: consen[i, j] = 1 where the labels agree."""
+    return GetConsensusEnsemble(np.asarray(clusters, dtype=np.int32)[None, :], tau=-1.0)
+
+
+def GetEnsemble(data, tol=0.01, n_comp=3, tau=0.3, range=(2, 20)):
+    """GetEnsemble(data, tol, n_comp, tau, range) of R/Clustering.R:125-154 -> truncated consensus matrix."""
+    lib = _lib.init()
+    s = _f64(data)
+    n = s.shape[0]
+    out = np.empty((n, n), dtype=np.float64, order="F")
+    _lib.check(lib.rsoptsc_get_ensemble(_dp(s), n, int(n_comp), float(tau), int(min(range)), int(max(range)), _dp(out)))
     return out
 
 

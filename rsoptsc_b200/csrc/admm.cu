@@ -299,6 +299,7 @@ void run_admm(const double* d_X, int64_t m, int64_t n, const Support& s, double 
       }
     }
     res.err2[it - 1] = err2;
+    report_progress(/*RSOPTSC_STAGE_ADMM*/ 0, it, res.err1[it - 1]);  // print("Err = ...") at R :191; interrupt point
     if (std::max(res.err1[it - 1], err2) <= epsilon) { res.stop = 3; break; }  // R :191-194
   }
   res.iters = it;

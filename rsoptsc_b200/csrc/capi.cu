@@ -151,6 +151,13 @@ static void resolve_phases() {
 
 void release_dense_scratch();
 
+static rsoptsc_progress_fn g_progress = nullptr;
+static void* g_progress_user = nullptr;
+void report_progress(int stage, int iter, double value) {
+  if (g_progress && g_progress(stage, iter, value, g_progress_user) != 0)
+    fail(RSOPTSC_STATUS_INTERRUPTED, __FILE__, __LINE__, "interrupted by the caller's progress callback");
+}
+
 template <class F>
 static int guarded(F&& f) {
   try {
@@ -189,6 +196,11 @@ int rsoptsc_finalize(void) {
   });
 }
 int64_t rsoptsc_kernel_launches(void) { return g_launches.load(); }
+int rsoptsc_set_progress(rsoptsc_progress_fn fn, void* user) {
+  g_progress = fn;
+  g_progress_user = user;
+  return 0;
+}
 int rsoptsc_timers_enable(int on) { g_timers_on = on != 0; return 0; }
 int rsoptsc_timers_reset(void) {
   resolve_phases();
@@ -497,6 +509,33 @@ int rsoptsc_similarity(const double* data, int64_t m, int64_t n, const double* e
   });
 }
 
+int rsoptsc_similarity_knn(const double* data, int64_t m, int64_t n, const int32_t* idx, int32_t K, double lambda,
+                           double* W, double* E, int32_t* iters) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(data && idx && m > 0 && n > 1, "similarity_knn: need a genes x cells matrix with at least 2 cells and a neighbour table");
+    RS_REQUIRE(K >= 1 && K <= n, "similarity_knn: K must be in [1, n]");
+    for (int64_t t = 0; t < n * K; ++t)
+      RS_REQUIRE(idx[t] >= 0 && idx[t] < n, "similarity_knn: neighbour index out of range (0-based, < n)");
+    DevBuf<double> d((size_t)m * n), X((size_t)m * n);
+    d.upload(data, (size_t)m * n, s);
+    normalize_columns(d.p, m, n, X.p);                           // a1
+    d.release();
+    SimOut out;
+    out.K = K;
+    build_support_from_idx(out.sup, idx, n, K);                  // :90-92 with the caller's IDX
+    run_admm(X.p, m, n, out.sup, lambda, out.st, out.res);       // a4-a10
+    if (W) {
+      DevBuf<double> w((size_t)n * n);
+      threshold_symmetrise_sparse(out.sup, out.st.Zs.p, w.p);    // a11
+      w.download(W, (size_t)n * n, s);
+      RS_CUDA(cudaStreamSynchronize(s));
+    }
+    if (E) *E = out.res.E;
+    if (iters) *iters = out.res.iters;
+  });
+}
+
 // ---- a12-a13 ----------------------------------------------------------------------------
 int rsoptsc_nmf_lee_dev(const double* d_V, int64_t n, int32_t k, int32_t max_iter, double* basis, double* coef,
                         int32_t* labels, int32_t* iters) {
@@ -559,6 +598,19 @@ int rsoptsc_count_clusters(const double* S, int64_t n, double tol, int32_t range
     DevBuf<double> d((size_t)n * n);
     d.upload(S, (size_t)n * n, s);
     count_clusters(d.p, n, tol, range_lo, range_hi, n_comp, upper_bound, lower_bound, vals, n_eigs);
+  });
+}
+
+int rsoptsc_get_ensemble(const double* S, int64_t n, int32_t n_comp, double tau, int32_t range_lo, int32_t range_hi,
+                         double* consen) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(S && consen && n > 0, "get_ensemble: empty matrix");
+    DevBuf<double> d((size_t)n * n), c((size_t)n * n);
+    d.upload(S, (size_t)n * n, s);
+    get_ensemble(d.p, n, n_comp, tau, range_lo, range_hi, c.p);
+    c.download(consen, (size_t)n * n, s);
+    RS_CUDA(cudaStreamSynchronize(s));
   });
 }
 
@@ -688,12 +740,13 @@ int rsoptsc_debug_gemm(int32_t op, const double* A, const double* B, double* C, 
                        int32_t backend, int32_t reps, double* ms_out) {
   return guarded([&] {
     cudaStream_t s = ctx().stream;
-    RS_REQUIRE(op >= 0 && op <= 3 && M > 0 && N > 0 && K > 0 && reps >= 1, "debug_gemm: bad arguments");
-    if (op == 0) N = M;
+    RS_REQUIRE(op >= 0 && op <= 4 && M > 0 && N > 0 && K > 0 && reps >= 1, "debug_gemm: bad arguments");
+    if (op == 0 || op == 4) N = M;
     const size_t na = (size_t)M * K, nb = op == 0 ? 0 : (size_t)N * K, nc = (size_t)M * N;
     DevBuf<double> a(na), b(std::max<size_t>(nb, 1)), c(nc);
     a.upload(A, na, s);
     if (nb) b.upload(B, nb, s);
+    if (op == 4) c.upload(C, nc, s);  // in/out: the update is applied 1 + reps times
     const int saved = gemm_backend();
     set_gemm_backend(backend);
     cudaEvent_t e0, e1;
@@ -703,6 +756,7 @@ int rsoptsc_debug_gemm(int32_t op, const double* A, const double* B, double* C, 
         case 0: gram_AtA(a.p, K, M, c.p); break;
         case 1: gemm_nn(a.p, b.p, c.p, M, N, K); break;
         case 2: gemm_nt(a.p, b.p, c.p, M, N, K); break;
+        case 4: syr2k_lower_sub(a.p, M, b.p, M, M, (int)K, c.p, M); break;
         default: gemm_tn(a.p, b.p, c.p, M, N, K); break;
       }
     };

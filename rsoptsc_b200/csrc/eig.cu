@@ -13,6 +13,7 @@
 #include <dlfcn.h>
 
 #include "comm.h"
+#include "gemm.h"
 #include "internal.h"
 #include "sytrd_kernel.cuh"
 #include "tridiag_bisect.h"
@@ -141,6 +142,12 @@ static int64_t native_min_n() {
   return t;
 }
 
+// trailing update of the tridiagonalisation on the library's own GEMM (tcgen05 split-integer kernel, gemm.cu)
+void sytrd_trailing_update(const double* V, long long ldv, const double* W, long long ldw, long long nr, int k, double* C,
+                           long long ldc) {
+  syr2k_lower_sub(V, ldv, W, ldw, nr, k, C, ldc);
+}
+
 static void sym_eig_native(double* d_A, int64_t n, double* d_lam, double keep_above = -1.0e300, bool collective = false) {
   Context& c = ctx();
   collective = collective && sharded();
@@ -155,6 +162,7 @@ static void sym_eig_native(double* d_A, int64_t n, double* d_lam, double keep_ab
     sytrd::Hooks hooks;
     Phase* panel_phase = nullptr;
     hooks.user = &panel_phase;
+    hooks.syr2k = sytrd_trailing_update;
     hooks.before = [](void* u, double bytes) {
       add_counter("sytrd_panel_bytes", bytes);
       *static_cast<Phase**>(u) = new Phase("sytrd_panel");
@@ -272,7 +280,9 @@ static void sym_eigvals_native(double* d_A, int64_t n, double* d_lam) {
     Phase ph("eig_sytrd");
     DevBuf<double> work(sytrd::workspace_doubles(n));
     int64_t launches = 0;
-    RS_CUDA(sytrd::run(c.cublas, c.stream, d_A, n, n, d.p, e.p, tau.p, work.p, &launches));
+    sytrd::Hooks hooks;
+    hooks.syr2k = sytrd_trailing_update;
+    RS_CUDA(sytrd::run(c.cublas, c.stream, d_A, n, n, d.p, e.p, tau.p, work.p, &launches, nullptr, &hooks));
     g_launches.fetch_add(launches, std::memory_order_relaxed);
   }
   Phase ph("eig_bisect");

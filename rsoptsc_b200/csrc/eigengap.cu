@@ -724,6 +724,43 @@ void pam(const double* d_P, int64_t n, int dim, int k, int32_t* h_labels, int32_
 }
 
 // ---- CountClusters ------------------------------------------------------------------------------
+// First half of GetEnsemble (R/Clustering.R:131-138): PCA scores of t(S), cluster::pam for every k in lo..hi.
+// table: (hi - lo + 1) x n row-major labels.
+static void ensemble_labels(const double* d_S, int64_t n, int n_comp, int lo, int hi, const Compressed& csr,
+                            const Compressed& csc, std::vector<int32_t>& table) {
+  DevBuf<double> scores((size_t)n * n_comp);
+  if (!(csr.nnz <= 128 * n && pca_scores_sparse(csr, csc, n, n_comp, scores.p))) {  // R :133, sparse route first
+    std::vector<double> eig;
+    pca_spectrum(d_S, n, n, eig, scores.p, n_comp);                       // R :133 (dense similarity)
+  }
+  const int R = hi - lo + 1;
+  table.assign((size_t)R * n, 0);
+  Phase ph("pam");
+  PamEngine eng;
+  eng.init(scores.p, n, n_comp, hi);
+  std::vector<int> med;
+  std::vector<int32_t> lab;
+  for (int k = lo; k <= hi; ++k) {                                        // R :136-138
+    eng.solve(k, med, lab);
+    std::copy(lab.begin(), lab.end(), table.begin() + (size_t)(k - lo) * n);
+  }
+}
+
+// GetEnsemble(data, tol, n_comp, tau, range = lo:hi) (R/Clustering.R:125-154): the truncated, symmetrised
+// ensemble consensus matrix, n x n on the device.
+void get_ensemble(const double* d_S, int64_t n, int n_comp, double tau, int lo, int hi, double* d_consen) {
+  RS_REQUIRE(lo >= 1 && hi >= lo && hi < n, "get_ensemble: invalid range");
+  RS_REQUIRE(n_comp >= 1 && n_comp <= n, "get_ensemble: invalid n_comp");
+  Compressed csr, csc;
+  compress(d_S, n, true, csr);
+  compress(d_S, n, false, csc);
+  std::vector<int32_t> table;
+  ensemble_labels(d_S, n, n_comp, lo, hi, csr, csc, table);
+  DevBuf<int32_t> d_table(table.size());
+  d_table.upload(table.data(), table.size(), ctx().stream);
+  consensus_dense(d_table.p, hi - lo + 1, n, tau, d_consen);              // R :143-153
+}
+
 void count_clusters(const double* d_S, int64_t n, double tol, int lo, int hi, int n_comp, int32_t* upper,
                     int32_t* lower, double* h_vals, int32_t* n_eigs) {
   cudaStream_t st = ctx().stream;
@@ -742,25 +779,9 @@ void count_clusters(const double* d_S, int64_t n, double tol, int lo, int hi, in
     for (double v : vals) solo += v <= tol;
   }
   const double tau = solo <= 5 ? 0.3 : (solo <= 10 ? 0.4 : 0.5);          // R :64-70
-  // GetEnsemble (R :125-154): PCA scores of t(S), PAM for every k in range, consensus
-  DevBuf<double> scores((size_t)n * n_comp);
-  if (!(csr.nnz <= 128 * n && pca_scores_sparse(csr, csc, n, n_comp, scores.p))) {  // R :133, sparse route first
-    std::vector<double> eig;
-    pca_spectrum(d_S, n, n, eig, scores.p, n_comp);                       // R :133 (dense similarity)
-  }
   const int R = hi - lo + 1;
-  std::vector<int32_t> table((size_t)R * n);
-  {
-    Phase ph("pam");
-    PamEngine eng;
-    eng.init(scores.p, n, n_comp, hi);
-    std::vector<int> med;
-    std::vector<int32_t> lab;
-    for (int k = lo; k <= hi; ++k) {                                      // R :136-138
-      eng.solve(k, med, lab);
-      std::copy(lab.begin(), lab.end(), table.begin() + (size_t)(k - lo) * n);
-    }
-  }
+  std::vector<int32_t> table;
+  ensemble_labels(d_S, n, n_comp, lo, hi, csr, csc, table);               // GetEnsemble, R :131-138
   if (getenv("RSOPTSC_EIGENGAP_DENSE")) {                                 // the literal route (tests compare the two)
     DevBuf<int32_t> d_table(table.size());
     d_table.upload(table.data(), table.size(), st);

@@ -28,4 +28,6 @@ void gemm_nt_ld(const double* A, int64_t lda, const double* B, int64_t ldb, doub
                 int64_t K);
 // C (M x N) = A^T * B, A: K x M, B: K x N
 void gemm_tn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
+// C (nr x nr, lower triangle) -= V W^T + W V^T, V and W nr x k (trailing update of the tridiagonalisation)
+void syr2k_lower_sub(const double* V, int64_t ldv, const double* W, int64_t ldw, int64_t nr, int k, double* C, int64_t ldc);
 }  // namespace rs

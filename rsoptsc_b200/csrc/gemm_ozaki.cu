@@ -264,8 +264,11 @@ k_ozaki_gemm(const __grid_constant__ CUtensorMap tmA_full, const __grid_constant
               TMEM_LD_32x32b_X32(taddr, r);
               asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
               const double w = pow2(-7 * p);
+              // int32 -> FP64 without the conversion pipe: the bit pattern 0x43300000'(x ^ 0x80000000) is the
+              // double 2^52 + 2^31 + x exactly, so one integer XOR and one FP64 subtraction replace I2F.F64
 #pragma unroll
-              for (int j = 0; j < 32; ++j) sum[j] += (double)(int)r[j] * w;
+              for (int j = 0; j < 32; ++j)
+                sum[j] += (__hiloint2double(0x43300000, (int)(r[j] ^ 0x80000000u)) - 4503601774854144.0) * w;
             }
             if (row < P.M) {
 #pragma unroll 4
@@ -530,6 +533,48 @@ void ozaki_gemm_nt_ld(const double* A, int64_t lda, const double* B, int64_t ldb
   oz::slice_operand(A, lda, M, K, /*contig=*/false, ozaki_slices(), a);
   oz::slice_operand(B, ldb, N, K, /*contig=*/false, ozaki_slices(), b);
   oz::run(a, b, C, M, N, ldc, false, false);
+}
+// ---- rank-2k update of the tridiagonalisation: C (nr x nr, lower triangle) -= V W^T + W V^T ---------------------
+// = [V | W] [-W | -V]^T, one accumulate-mode launch over the lower tiles.  The operands are packed side by side first
+// (nr x 2k each) so that one slicing pass per operand covers both halves; 2k = 128 is only four k-blocks, so the
+// launch is bound by its epilogue (read-modify-write of C), like the cuBLAS rank-2k update it replaces, but runs the
+// products at tensor-core rate.
+namespace oz {
+__global__ void k_pack_syr2k(const double* __restrict__ V, long long ldv, const double* __restrict__ W, long long ldw, int nr, int k,
+                             double* __restrict__ P, double* __restrict__ Q) {
+  const int c = blockIdx.y;  // 0 .. 2k-1
+  const double* src = c < k ? V + (long long)c * ldv : W + (long long)(c - k) * ldw;
+  const double* neg = c < k ? W + (long long)c * ldw : V + (long long)(c - k) * ldv;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += gridDim.x * blockDim.x) {
+    P[i + (size_t)c * nr] = src[i];
+    Q[i + (size_t)c * nr] = -neg[i];
+  }
+}
+// small trailing blocks: one thread per lower-triangle entry
+__global__ void k_syr2k_small(const double* __restrict__ V, long long ldv, const double* __restrict__ W, long long ldw, int nr, int k,
+                              double* __restrict__ C, long long ldc) {
+  const int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y;
+  if (i >= nr || j > i) return;
+  double acc = 0;
+  for (int t = 0; t < k; ++t)
+    acc += V[i + (long long)t * ldv] * W[j + (long long)t * ldw] + W[i + (long long)t * ldw] * V[j + (long long)t * ldv];
+  C[i + (long long)j * ldc] -= acc;
+}
+}  // namespace oz
+void ozaki_syr2k_lower_sub(const double* V, int64_t ldv, const double* W, int64_t ldw, int64_t nr, int k, double* C, int64_t ldc) {
+  if (nr < 1 || k < 1) return;
+  if (nr < 384) {
+    dim3 grid((unsigned)cdiv(nr, 32), (unsigned)cdiv(nr, 8)), block(32, 8);
+    RS_LAUNCH(oz::k_syr2k_small, grid, block, 0, V, (long long)ldv, W, (long long)ldw, (int)nr, k, C, (long long)ldc);
+    return;
+  }
+  DevBuf<double> P((size_t)nr * 2 * k), Q((size_t)nr * 2 * k);
+  dim3 grid((unsigned)std::min<int64_t>(cdiv(nr, 256), 64), (unsigned)(2 * k));
+  RS_LAUNCH(oz::k_pack_syr2k, grid, 256, 0, V, (long long)ldv, W, (long long)ldw, (int)nr, k, P.p, Q.p);
+  oz::Operand a, b;
+  oz::slice_operand(P.p, nr, nr, 2 * k, /*contig=*/false, ozaki_slices(), a);
+  oz::slice_operand(Q.p, nr, nr, 2 * k, /*contig=*/false, ozaki_slices(), b);
+  oz::run(a, b, C, nr, nr, ldc, /*lower_only=*/true, /*accumulate=*/true);
 }
 void ozaki_gemm_tn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K) {
   oz::Operand a, b;

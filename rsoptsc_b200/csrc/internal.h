@@ -17,6 +17,9 @@ struct Phase {  // RAII: device time of a region on the library stream
   ~Phase();
 };
 
+// progress / interrupt hook of the C ABI (rsoptsc_set_progress): throws Error(7) when the caller asks to stop
+void report_progress(int stage, int iter, double value);
+
 #define RS_LAUNCH(kernel, grid, block, smem, ...)                                   \
   do {                                                                              \
     kernel<<<(grid), (block), (smem), ::rs::ctx().stream>>>(__VA_ARGS__);           \
@@ -186,6 +189,7 @@ void signaling_pair(const double* d_lig, const double* d_rec, const double* d_be
 // eigengap.cu
 void get_components(const double* d_S, int64_t n, double tol, double* h_vals, int32_t* n_eigs);
 void consensus_dense(const int32_t* d_labels, int R, int64_t n, double tau, double* d_consen);
+void get_ensemble(const double* d_S, int64_t n, int n_comp, double tau, int lo, int hi, double* d_consen);
 void pam(const double* d_P, int64_t n, int dim, int k, int32_t* h_labels, int32_t* h_medoids);
 void count_clusters(const double* d_S, int64_t n, double tol, int lo, int hi, int n_comp,
                     int32_t* upper, int32_t* lower, double* h_vals, int32_t* n_eigs);

@@ -384,6 +384,7 @@ void nmf_lee(const double* d_V, int64_t n, int k, int max_iter, double* h_basis,
         have_prev = true;
         inc = 0;
       }
+      report_progress(/*RSOPTSC_STAGE_NMF*/ 1, it, 0.0);  // interrupt point between stop checks
       if (inc > stop_conv) break;
     }
   }

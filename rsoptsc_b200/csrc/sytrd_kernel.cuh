@@ -23,7 +23,8 @@
 //    results are bit-reproducible;
 //  * while a CTA waits in the all-reduce that precedes the product phase (DRAM idle), its warps
 //    stage the first strip of their run in shared memory with cp.async;
-//  * the rank-2NB trailing update between panels is one cublasDsyr2k.
+//  * the rank-2NB trailing update between panels runs on the tcgen05 split-integer GEMM (Hooks::syr2k; the
+//    stand-alone probes fall back to cublasDsyr2k).
 //
 // HBM traffic: sum_j 4 (n-j)^2 = (4/3) n^3 bytes for the products (the floor of any one-stage
 // tridiagonalisation) + 16 n^3 / (3 NB) for the trailing updates.
@@ -636,7 +637,22 @@ struct Hooks {  // optional instrumentation around every panel launch (phase tim
   void (*before)(void* user, double algorithmic_bytes) = nullptr;
   void (*after)(void* user) = nullptr;
   void* user = nullptr;
+  // trailing update C(lower, nr x nr) -= V W^T + W V^T on the caller's own GEMM (the library passes its tcgen05
+  // split-integer kernel, gemm_ozaki.cu); null: cublasDsyr2k (stand-alone probes)
+  void (*syr2k)(const double* V, long long ldv, const double* W, long long ldw, long long nr, int k, double* C,
+                long long ldc) = nullptr;
 };
+inline cudaError_t trailing_update(cublasHandle_t blas, const Hooks* hooks, const double* V, long long ldv, const double* W,
+                                   long long ldw, long long nr, int k, double* C, long long ldc) {
+  if (hooks && hooks->syr2k) {
+    hooks->syr2k(V, ldv, W, ldw, nr, k, C, ldc);
+    return cudaSuccess;
+  }
+  const double mone = -1.0, one = 1.0;
+  cublasStatus_t bs = cublasDsyr2k(blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)nr, k, &mone, V, (int)ldv, W, (int)ldw, &one,
+                                   C, (int)ldc);
+  return bs == CUBLAS_STATUS_SUCCESS ? cudaSuccess : cudaErrorUnknown;
+}
 inline cudaError_t run(cublasHandle_t blas, cudaStream_t stream, double* A, int64_t n, int64_t lda, double* d, double* e,
                        double* tau, double* work, int64_t* launches, long long* prof = nullptr, const Hooks* hooks = nullptr) {
   if (n < 1) return cudaSuccess;
@@ -681,10 +697,8 @@ inline cudaError_t run(cublasHandle_t blas, cudaStream_t stream, double* A, int6
     if (launches) ++*launches;
     const int64_t r0 = j0 + pw, nr = n - r0;  // trailing block
     if (nr > 0) {
-      const double mone = -1.0, one = 1.0;
-      cublasStatus_t bs = cublasDsyr2k(blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)nr, pw, &mone, A + r0 + j0 * lda,
-                                       (int)lda, P.W + r0, (int)n, &one, A + r0 + r0 * lda, (int)lda);
-      if (bs != CUBLAS_STATUS_SUCCESS) return cudaErrorUnknown;
+      st = trailing_update(blas, hooks, A + r0 + j0 * lda, lda, P.W + r0, n, nr, pw, A + r0 + r0 * lda, lda);
+      if (st != cudaSuccess) return st;
     }
   }
   k_restore_subdiag<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(A, lda, (int)n, e, d);

@@ -7,6 +7,9 @@
 
 namespace rs {
 
+void sytrd_trailing_update(const double* V, long long ldv, const double* W, long long ldw, long long nr, int k, double* C,
+                           long long ldc);  // eig.cu
+
 static int64_t mg_min_n() {
   // the exchange adds ~3 us per column; the product phase of a column takes 14.5 us (n / 7,954)^2 on one GPU and
   // 1/P of that on P: below these sizes the exchange costs more than it saves
@@ -45,6 +48,7 @@ void sytrd_mg_run(double* d_A, int64_t n, double* d_d, double* d_e, double* d_ta
   sytrd::Hooks hooks;
   Phase* panel_phase = nullptr;
   hooks.user = &panel_phase;
+  hooks.syr2k = sytrd_trailing_update;
   hooks.before = [](void* u, double bytes) {
     add_counter("sytrd_panel_bytes", bytes);
     *static_cast<Phase**>(u) = new Phase("sytrd_panel");

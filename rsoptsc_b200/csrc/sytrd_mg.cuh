@@ -519,10 +519,8 @@ inline cudaError_t run_mg(cublasHandle_t blas, cudaStream_t stream, double* A, i
     if (launches) ++*launches;
     const int64_t r0 = j0 + pw, nr = n - r0;
     if (nr > 0) {
-      const double mone = -1.0, one = 1.0;
-      cublasStatus_t bs = cublasDsyr2k(blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)nr, pw, &mone, A + r0 + j0 * lda,
-                                       (int)lda, P.W + r0, (int)n, &one, A + r0 + r0 * lda, (int)lda);
-      if (bs != CUBLAS_STATUS_SUCCESS) return cudaErrorUnknown;
+      st = trailing_update(blas, hooks, A + r0 + j0 * lda, lda, P.W + r0, n, nr, pw, A + r0 + r0 * lda, lda);
+      if (st != cudaSuccess) return st;
     }
   }
   k_restore_subdiag<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(A, lda, (int)n, e, d);

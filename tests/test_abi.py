@@ -24,7 +24,7 @@ def test_header_symbols_are_exported(lib):
     for name in names:
         assert hasattr(lib, name), "missing export " + name
     assert sorted(_lib.SIGNATURES) == names, "ctypes table out of sync with the header"
-    assert lib.rsoptsc_abi_version() == 2
+    assert lib.rsoptsc_abi_version() == 3
 
 
 def test_no_reference_to_oracle_in_product():

@@ -697,3 +697,61 @@ def test_computeM_err_trace_matches_oracle_golden():
     assert np.allclose(r["Err"][:k, 0], g["err1"], rtol=1e-8, atol=1e-12)
     Zs = r["Z"][np.arange(n)[:, None], g["idx"]]
     assert relF(Zs, g["Zs"]) < 1e-6
+
+
+# ---- boundary completeness ----------------------------------------------------------
+@pytest.mark.gpu
+def test_similarity_with_caller_neighbour_table():
+    """use_umap_indices = TRUE (R/SimilarityM.R:85-87): the caller's IDX replaces the kNN search.  The table here is
+    NOT a kNN table of any embedding (random neighbours, K = 12), so only the supplied one can give the answer."""
+    p = small_problem(120, 260, seed=17)
+    n = p["data"].shape[1]
+    rng = np.random.default_rng(4)
+    idx = np.stack([np.concatenate(([j], rng.choice(np.delete(np.arange(n), j), 11, replace=False))) for j in range(n)])
+    ref = O.computeM(O.mask_from_idx(idx, n), p["X"], 0.5, literal=False)
+    Wref = O.threshold_symmetrise(ref["Z"])
+    got = api.SimilarityM(0.5, p["data"], knn_indices=idx)
+    assert got["iters"] == ref["iters"] and got["K"] == 12
+    assert abs(got["E"] - ref["E"]) <= 1e-9 * ref["E"]
+    assert relF(got["W"], Wref) < 1e-6
+    with pytest.raises(Exception):
+        api.SimilarityM(0.5, p["data"], knn_indices=idx + n)      # out-of-range indices are rejected
+
+
+@pytest.mark.gpu
+def test_progress_callback_reports_err_and_interrupts():
+    """rsoptsc_set_progress: one call per ADMM iteration carrying Err[iter, 1] (the value R prints at
+    R/SimilarityM.R:191), NMF stop checks every 10 iterations, and a non-zero return stops the run (status 7)."""
+    from rsoptsc_b200 import _lib
+    p = small_problem(100, 220, seed=23)
+    seen = []
+    api.set_progress(lambda stage, it, v: seen.append((stage, it, v)) and False)
+    try:
+        r = api.computeM(None, p["X"], 0.5, idx=p["idx"])
+        admm = [s for s in seen if s[0] == 0]
+        assert len(admm) in (r["iters"] - 1, r["iters"])                  # an "error min" stop returns before :190
+        assert [s[1] for s in admm] == list(range(1, len(admm) + 1))
+        assert np.allclose([s[2] for s in admm], r["Err"][:len(admm), 0], rtol=0, atol=0)
+        seen.clear()
+        W = api.threshold_symmetrise(r["Z"])
+        c = api.nmf_lee(W, 5)
+        nmf = [s for s in seen if s[0] == 1]
+        assert [s[1] for s in nmf] == list(range(10, c["iters"] + 1, 10))
+        api.set_progress(lambda stage, it, v: stage == 0 and it == 3)
+        with pytest.raises(_lib.RsoptscError, match="error 7"):
+            api.computeM(None, p["X"], 0.5, idx=p["idx"])
+    finally:
+        api.set_progress(None)
+    again = api.computeM(None, p["X"], 0.5, idx=p["idx"])                   # the library is usable after an interrupt
+    assert again["iters"] == r["iters"] and relF(again["Z"], r["Z"]) == 0.0
+
+
+@pytest.mark.gpu
+def test_get_ensemble_and_consensus_fixture(joost):
+    """GetEnsemble / GetConsensus (R/Clustering.R:125-175) on the reference's own similarity matrix."""
+    S = joost["S"]
+    ref = O.GetEnsemble(S, tol=0.01, tau=0.4, n_comp=3)
+    got = api.GetEnsemble(S, tol=0.01, n_comp=3, tau=0.4)
+    assert np.array_equal(got, ref)
+    lab = np.asarray(joost["labels"], dtype=np.int32)
+    assert np.array_equal(api.GetConsensus(lab), O.GetConsensus(lab))
