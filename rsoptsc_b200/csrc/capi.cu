@@ -158,9 +158,15 @@ void report_progress(int stage, int iter, double value) {
     fail(RSOPTSC_STATUS_INTERRUPTED, __FILE__, __LINE__, "interrupted by the caller's progress callback");
 }
 
+// One caller at a time: the context, the caching allocator, the phase tables and the per-function statics are
+// shared, unsynchronised state (an R host is single-threaded anyway; Python hosts with threads serialise here).
+// The process's current device is re-asserted on every entry: a host such as torch may have switched it.
+static std::recursive_mutex g_api_mutex;
 template <class F>
 static int guarded(F&& f) {
+  std::lock_guard<std::recursive_mutex> lock(g_api_mutex);
   try {
+    if (g_ctx.initialized) cudaSetDevice(g_ctx.device);
     f();
     return 0;
   } catch (const Error& e) {
@@ -326,7 +332,9 @@ int rsoptsc_pca_spectrum(const double* X, int64_t m, int64_t n, double* eig, int
 int rsoptsc_knn(const double* emb, int64_t n, int32_t dim, int32_t K, int32_t* idx) {
   return guarded([&] {
     cudaStream_t s = ctx().stream;
-    RS_REQUIRE(n > 0, "knn: empty embedding");
+    RS_REQUIRE(emb && idx && n > 0, "knn: empty embedding");
+    RS_REQUIRE(dim >= 1 && dim <= 3, "knn: dim must be in [1, 3]");
+    RS_REQUIRE(K >= 1 && K <= 32 && K <= n, "knn: K must be in [1, min(32, n)]");
     DevBuf<double> e((size_t)n * dim);
     DevBuf<int32_t> out((size_t)n * K);
     e.upload(emb, (size_t)n * dim, s);

@@ -32,6 +32,7 @@ constexpr int STAGE_BYTES = 2 * OPER_BYTES;       // 64 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int THREADS = 192;
 constexpr int ROWPAD = 128;
+constexpr int EX_BAD = 1 << 20;  // == EX_NONFINITE (slicing section): operand row with NaN / Inf
 
 struct Params {
   double* C;
@@ -275,7 +276,9 @@ k_ozaki_gemm(const __grid_constant__ CUtensorMap tmA_full, const __grid_constant
               for (int j = 0; j < 32; ++j) {
                 const int col = t.y * BN + c0 + j;
                 if (col < P.N) {
-                  const double v = sum[j] * pow2(exa + P.exB[col]);
+                  const int exb = P.exB[col];
+                  const double v = (exa >= EX_BAD || exb >= EX_BAD) ? __longlong_as_double(0x7ff8000000000000LL)
+                                                                     : sum[j] * pow2(exa + exb);
                   double* dst = P.C + (size_t)row + (size_t)col * P.ldc;
                   *dst = (first && !P.accumulate) ? v : (*dst + v);
                 }
@@ -302,11 +305,18 @@ k_ozaki_gemm(const __grid_constant__ CUtensorMap tmA_full, const __grid_constant
 // ---- slicing ------------------------------------------------------------------------------------
 // Operand row r, contraction index k.  contig: x = X[k + r*ld] (K runs down a column of X);
 // otherwise x = X[r + k*ld].  Q[t][r][k] (int8, k contiguous, padded with zeros).
+// A row holding NaN or Inf gets the sentinel exponent EX_NONFINITE: the epilogue then writes NaN into every output
+// that row takes part in, as an FP64 GEMM would, instead of a finite but meaningless number (fmax drops NaN).
+constexpr int EX_NONFINITE = EX_BAD;
+__device__ __forceinline__ double abs_or_inf(double x) {
+  const double a = fabs(x);
+  return a == a ? a : INFINITY;  // NaN -> Inf so that it survives the fmax reductions
+}
 __global__ void k_rowmax_contig(const double* __restrict__ X, int64_t ld, int R, int K, int* __restrict__ ex) {
   __shared__ double sm[8];
   const int r = blockIdx.x;
   double mx = 0;
-  for (int k = threadIdx.x; k < K; k += 256) mx = fmax(mx, fabs(X[(int64_t)k + (int64_t)r * ld]));
+  for (int k = threadIdx.x; k < K; k += 256) mx = fmax(mx, abs_or_inf(X[(int64_t)k + (int64_t)r * ld]));
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
   __syncthreads();
@@ -314,7 +324,7 @@ __global__ void k_rowmax_contig(const double* __restrict__ X, int64_t ld, int R,
     for (int w = 1; w < 8; ++w) mx = fmax(mx, sm[w]);
     int e = 0;
     if (mx > 0 && isfinite(mx)) frexp(mx, &e);  // mx = f * 2^e, f in [0.5, 1)
-    ex[r] = e;
+    ex[r] = isfinite(mx) ? e : EX_NONFINITE;
   }
 }
 __global__ void k_rowmax_strided(const double* __restrict__ X, int64_t ld, int R, int K, int* __restrict__ ex) {
@@ -322,10 +332,10 @@ __global__ void k_rowmax_strided(const double* __restrict__ X, int64_t ld, int R
   if (r >= R) return;
   double mx = 0;
 #pragma unroll 8
-  for (int k = 0; k < K; ++k) mx = fmax(mx, fabs(X[(int64_t)r + (int64_t)k * ld]));
+  for (int k = 0; k < K; ++k) mx = fmax(mx, abs_or_inf(X[(int64_t)r + (int64_t)k * ld]));
   int e = 0;
   if (mx > 0 && isfinite(mx)) frexp(mx, &e);
-  ex[r] = e;
+  ex[r] = isfinite(mx) ? e : EX_NONFINITE;
 }
 __device__ __forceinline__ void slice_value(double x, int e, int S, int8_t* out) {
   double v = x * pow2(-e);  // |v| < 1, exact

@@ -755,3 +755,32 @@ def test_get_ensemble_and_consensus_fixture(joost):
     assert np.array_equal(got, ref)
     lab = np.asarray(joost["labels"], dtype=np.int32)
     assert np.array_equal(api.GetConsensus(lab), O.GetConsensus(lab))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("backend", [0, 2])
+def test_gemm_propagates_nonfinite_operands(backend):
+    """a NaN / Inf operand entry must poison the outputs it takes part in on both GEMM backends (the
+    split-integer kernel used to clamp it to a finite slice)."""
+    import ctypes as C
+    from rsoptsc_b200 import _lib
+    lib = _lib.init()
+    rng = np.random.default_rng(0)
+    M = N = K = 300
+    A = np.asfortranarray(rng.standard_normal((M, K)))
+    B = np.asfortranarray(rng.standard_normal((K, N)))
+    A[5, 7] = np.nan
+    B[11, 3] = np.inf
+    Cc = np.zeros((M, N), order="F")
+    dp = _lib.c_double_p
+    _lib.check(lib.rsoptsc_debug_gemm(1, A.ctypes.data_as(dp), B.ctypes.data_as(dp), Cc.ctypes.data_as(dp), M, N, K,
+                                      backend, 1, None))
+    assert np.isnan(Cc[5, :]).all()
+    assert not np.isfinite(Cc[:, 3]).any()
+    ok = np.ones((M, N), dtype=bool)
+    ok[5, :] = False
+    ok[:, 3] = False
+    assert np.isfinite(Cc[ok]).all()
+    ref = np.delete(np.delete(A, 5, axis=0) @ np.delete(B, 3, axis=1), [], axis=0)
+    got = np.delete(np.delete(Cc, 5, axis=0), 3, axis=1)
+    assert relF(got, ref) < 1e-12
