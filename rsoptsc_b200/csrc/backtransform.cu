@@ -47,15 +47,25 @@ void apply_q_left(const double* d_A, int64_t lda, const double* d_tau, int64_t n
   for (int64_t k = nblk - 1; k >= 0; --k) {
     const int64_t j0 = k * nb, nbk = std::min(nb, nref - j0), r0 = j0 + 1, m = n - r0;
     dim3 ge((unsigned)std::min<int64_t>(cdiv(m, 256), 256), (unsigned)nbk);
-    RS_LAUNCH(k_extract_V, ge, 256, 0, d_A, (long long)lda, (int)j0, (int)nbk, (int)m, Vb.p);
-    gram_AtA(Vb.p, m, nbk, S.p);  // lower triangle of V^T V
-    dim3 gu((unsigned)cdiv(nbk, 128), (unsigned)nbk);
-    RS_LAUNCH(k_build_U, gu, 128, 0, S.p, d_tau + j0, (int)nbk, U.p);
+    {
+      Phase ph("bt_gram");
+      RS_LAUNCH(k_extract_V, ge, 256, 0, d_A, (long long)lda, (int)j0, (int)nbk, (int)m, Vb.p);
+      gram_AtA(Vb.p, m, nbk, S.p);  // lower triangle of V^T V
+      dim3 gu((unsigned)cdiv(nbk, 128), (unsigned)nbk);
+      RS_LAUNCH(k_build_U, gu, 128, 0, S.p, d_tau + j0, (int)nbk, U.p);
+    }
     double* Zr = d_Z + r0;
-    gemm_tn_ld(Vb.p, m, Zr, n, X.p, nbk, nbk, ncols, m);  // X = V^T Z            (nbk x ncols)
-    const double mone = -1.0;
-    RS_CUBLAS(cublasDtrsm(c.cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)nbk, (int)ncols,
-                          &mone, U.p, (int)nbk, X.p, (int)nbk));  // X <- -T X
+    {
+      Phase ph("bt_vtz");
+      gemm_tn_ld(Vb.p, m, Zr, n, X.p, nbk, nbk, ncols, m);  // X = V^T Z            (nbk x ncols)
+    }
+    {
+      Phase ph("bt_trsm");
+      const double mone = -1.0;
+      RS_CUBLAS(cublasDtrsm(c.cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)nbk,
+                            (int)ncols, &mone, U.p, (int)nbk, X.p, (int)nbk));  // X <- -T X
+    }
+    Phase ph("bt_update");
     gemm_nn_ld_acc(Vb.p, m, X.p, nbk, Zr, n, m, ncols, nbk);  // Z += V (-T V^T Z)
   }
 }

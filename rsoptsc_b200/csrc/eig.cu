@@ -201,13 +201,13 @@ static void sym_eig_native(double* d_A, int64_t n, double* d_lam, double keep_ab
     RS_CUDA(cudaStreamSynchronize(c.stream));
   } else if (ncols > 0) {
     Phase ph("eig_backtransform");
-    // cusolverDnDormtr (38 ms at 7,954 rows) is still ahead of the own blocked back-transformation (49 ms: its
-    // panel-shaped GEMMs run at ~33 TF/s-eq) but overflows its 32-bit workspace above 32,768 rows.
-    // RSOPTSC_BACKTRANSFORM=native|cusolver forces one of them (tests).
+    // Own blocked compact-WY back-transformation (backtransform.cu, panel GEMMs on tcgen05): 41 ms at 7,954 rows
+    // against cusolverDnDormtr's 47 ms since the GEMM epilogue keeps its loads in flight, and no 32-bit workspace
+    // limit.  RSOPTSC_BACKTRANSFORM=cusolver keeps the library routine for comparison (tests).
     static int use_lib = -1;
     if (use_lib < 0) {
       const char* e = getenv("RSOPTSC_BACKTRANSFORM");
-      use_lib = (e && std::string(e) == "native") ? 0 : 1;
+      use_lib = (e && std::string(e) == "cusolver") ? 1 : 0;
     }
     if (use_lib && n <= 32768) {
       int lwork = 0;

@@ -13,7 +13,8 @@
 //               streaming the 36 pair-GEMMs one after another)
 //   warp 1      MMA issuer (one elected thread): tcgen05.mma.kind::i8 M128 N128 K32, the S/2 group
 //               accumulators of a pass live side by side in TMEM (4 x 128 columns = 512)
-//   warps 2-5   epilogue: tcgen05.ld, int32 -> FP64, scale by 2^(exA_i + exB_j - 7p), read-modify-write C
+//   warps 2-9   epilogue (two warps per TMEM lane quarter, 64 columns each): tcgen05.ld, int32 -> FP64, scale by
+//               2^(exA_i + exB_j - 7p), store / read-modify-write C with all loads of a 32-column chunk in flight
 // Two passes per tile: groups p > S/2+1 (need all slices), then the S/2 low groups (slices 1..S/2).
 #include <cuda.h>
 
@@ -30,7 +31,8 @@ constexpr int SLICE_TILE = BM * BK;               // 4 KB: one slice of one oper
 constexpr int OPER_BYTES = MAXS * SLICE_TILE;     // 32 KB
 constexpr int STAGE_BYTES = 2 * OPER_BYTES;       // 64 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int EPI_WARPS = THREADS / 32 - 2;
 constexpr int ROWPAD = 128;
 constexpr int EX_BAD = 1 << 20;  // == EX_NONFINITE (slicing section): operand row with NaN / Inf
 
@@ -40,6 +42,8 @@ struct Params {
   const int* exB;
   const int2* tiles;
   int num_tiles, M, N, ldc, kblocks, S, accumulate;
+  int b_kshift;  // B's k-block = (A's k-block + b_kshift) mod kblocks: [V | W] against [W | V] from ONE sliced operand
+  int negate;    // C -= A B^T instead of +=
 };
 
 // ---- PTX helpers -----------------------------------------------------------------------------
@@ -114,6 +118,15 @@ __device__ __forceinline__ uint32_t make_idesc() {
       : "r"(taddr)                                                                                            \
       : "memory")
 
+#define TMEM_LD_32x32b_X16(taddr, r)                                                                          \
+  asm volatile(                                                                                               \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                               \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                        \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),       \
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) \
+      : "r"(taddr)                                                                                            \
+      : "memory")
+
 __device__ __forceinline__ double pow2(int e) {
   e = max(-1022, min(1023, e));
   return __hiloint2double((e + 1023) << 20, 0);
@@ -167,7 +180,7 @@ k_ozaki_gemm(const __grid_constant__ CUtensorMap tmA_full, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 4);
+    mbar_init(tmem_empty, EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM)
@@ -198,7 +211,9 @@ k_ozaki_gemm(const __grid_constant__ CUtensorMap tmA_full, const __grid_constant
               mbar_expect_tx(full_bar(stage), bytes);
               const uint32_t sa = base + stage * STAGE_BYTES;
               tma_load_3d(sa, pass == 0 ? &tmA_full : &tmA_half, full_bar(stage), kb * BK, t.x * BM, 0);
-              tma_load_3d(sa + OPER_BYTES, pass == 0 ? &tmB_full : &tmB_half, full_bar(stage), kb * BK, t.y * BN, 0);
+              int kbB = kb + P.b_kshift;
+              if (kbB >= kb_total) kbB -= kb_total;
+              tma_load_3d(sa + OPER_BYTES, pass == 0 ? &tmB_full : &tmB_half, full_bar(stage), kbB * BK, t.y * BN, 0);
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
           }
@@ -241,8 +256,10 @@ k_ozaki_gemm(const __grid_constant__ CUtensorMap tmA_full, const __grid_constant
     }
     __syncwarp();
   } else {
-    // ================= epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =================
+    // ================= epilogue (warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4) =====
+    // Two warps per SM sub-partition: while one waits for its C loads or a TMEM read the other issues.
     const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
     uint32_t acc_phase = 0;
     for (int ti = blockIdx.x; ti < P.num_tiles; ti += gridDim.x) {
       const int2 t = P.tiles[ti];
@@ -255,33 +272,49 @@ k_ozaki_gemm(const __grid_constant__ CUtensorMap tmA_full, const __grid_constant
           pass_groups(S, pass, p_lo, p_hi);
           mbar_wait(tmem_full, acc_phase);
           tc_fence_after();
-          for (int c0 = 0; c0 < BN; c0 += 32) {
+          // Read-modify-write only where C already holds something (the second pass of a unit, or accumulate
+          // mode); the first pass of a plain GEMM stores without reading.  All 32 loads of a chunk are issued
+          // before the TMEM reads so that they are in flight together (the epilogue runs one warp per SM
+          // sub-partition: nothing else hides their latency), and every loop over j is fully unrolled so that
+          // sum[] and cold[] stay in registers.
+          const bool rmw = !(first && !P.accumulate);
+          for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
+            const int colbase = t.y * BN + c0;
+            const int exb_lane = (colbase + lane < P.N) ? P.exB[colbase + lane] : 0;
+            double* const dst0 = P.C + (size_t)row + (size_t)colbase * P.ldc;
+            double cold[32];
+            if (rmw) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                cold[j] = (row < P.M && colbase + j < P.N) ? __ldcg(dst0 + (size_t)j * P.ldc) : 0.0;
+            }
             double sum[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) sum[j] = 0.0;
             for (int p = p_hi; p >= p_lo; --p) {  // smallest contributions first
-              uint32_t r[32];
               const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((p - p_lo) * BN + c0);
-              TMEM_LD_32x32b_X32(taddr, r);
-              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
               const double w = pow2(-7 * p);
               // int32 -> FP64 without the conversion pipe: the bit pattern 0x43300000'(x ^ 0x80000000) is the
               // double 2^52 + 2^31 + x exactly, so one integer XOR and one FP64 subtraction replace I2F.F64
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                sum[j] += (__hiloint2double(0x43300000, (int)(r[j] ^ 0x80000000u)) - 4503601774854144.0) * w;
+              for (int h = 0; h < 2; ++h) {
+                uint32_t r[16];
+                TMEM_LD_32x32b_X16(taddr + 16u * h, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  sum[16 * h + j] += (__hiloint2double(0x43300000, (int)(r[j] ^ 0x80000000u)) - 4503601774854144.0) * w;
+              }
             }
-            if (row < P.M) {
-#pragma unroll 4
-              for (int j = 0; j < 32; ++j) {
-                const int col = t.y * BN + c0 + j;
-                if (col < P.N) {
-                  const int exb = P.exB[col];
-                  const double v = (exa >= EX_BAD || exb >= EX_BAD) ? __longlong_as_double(0x7ff8000000000000LL)
-                                                                     : sum[j] * pow2(exa + exb);
-                  double* dst = P.C + (size_t)row + (size_t)col * P.ldc;
-                  *dst = (first && !P.accumulate) ? v : (*dst + v);
-                }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int exb = __shfl_sync(0xffffffffu, exb_lane, j);
+              if (row < P.M && colbase + j < P.N) {
+                double v = (exa >= EX_BAD || exb >= EX_BAD) ? __longlong_as_double(0x7ff8000000000000LL)
+                                                             : sum[j] * pow2(exa + exb);
+                if (P.negate) v = -v;
+                if (rmw) v += cold[j];
+                dst0[(size_t)j * P.ldc] = v;
               }
             }
           }
@@ -438,7 +471,7 @@ static CUtensorMap make_map(const Operand& op, int depth) {
 }
 
 static void run(const Operand& a, const Operand& b, double* C, int64_t M, int64_t N, int64_t ldc, bool lower_only,
-                bool accumulate) {
+                bool accumulate, int b_kshift = 0, bool negate = false) {
   RS_REQUIRE(a.Kp == b.Kp && a.S == b.S, "ozaki: operand mismatch");
   const int tm = (int)cdiv(M, BM), tn = (int)cdiv(N, BN);
   // Rasterise in G x G super-blocks: the ~148 tiles in flight then share G panels of A rows and G
@@ -456,6 +489,8 @@ static void run(const Operand& a, const Operand& b, double* C, int64_t M, int64_
   Params P;
   P.C = C; P.exA = a.ex.p; P.exB = b.ex.p; P.tiles = d_tiles.p; P.num_tiles = (int)tiles.size();
   P.M = (int)M; P.N = (int)N; P.ldc = (int)ldc; P.kblocks = (int)(a.Kp / BK); P.S = a.S; P.accumulate = accumulate ? 1 : 0;
+  P.b_kshift = b_kshift; P.negate = negate ? 1 : 0;
+  RS_REQUIRE(b_kshift >= 0 && b_kshift < std::max(P.kblocks, 1), "ozaki: bad k shift");
   const CUtensorMap mAf = make_map(a, a.S), mAh = make_map(a, a.S / 2), mBf = make_map(b, b.S), mBh = make_map(b, b.S / 2);
   static bool attr_set = false;
   if (!attr_set) {
@@ -545,19 +580,51 @@ void ozaki_gemm_nt_ld(const double* A, int64_t lda, const double* B, int64_t ldb
   oz::run(a, b, C, M, N, ldc, false, false);
 }
 // ---- rank-2k update of the tridiagonalisation: C (nr x nr, lower triangle) -= V W^T + W V^T ---------------------
-// = [V | W] [-W | -V]^T, one accumulate-mode launch over the lower tiles.  The operands are packed side by side first
-// (nr x 2k each) so that one slicing pass per operand covers both halves; 2k = 128 is only four k-blocks, so the
-// launch is bound by its epilogue (read-modify-write of C), like the cuBLAS rank-2k update it replaces, but runs the
-// products at tensor-core rate.
+// = -[V | W] [W | V]^T, one accumulate-mode launch over the lower tiles.  128 contraction entries are only four
+// k-blocks, so the launch is bound by its epilogue (read-modify-write of C) like the cuBLAS rank-2k update it replaces.
 namespace oz {
-__global__ void k_pack_syr2k(const double* __restrict__ V, long long ldv, const double* __restrict__ W, long long ldw, int nr, int k,
-                             double* __restrict__ P, double* __restrict__ Q) {
-  const int c = blockIdx.y;  // 0 .. 2k-1
-  const double* src = c < k ? V + (long long)c * ldv : W + (long long)(c - k) * ldw;
-  const double* neg = c < k ? W + (long long)c * ldw : V + (long long)(c - k) * ldv;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += gridDim.x * blockDim.x) {
-    P[i + (size_t)c * nr] = src[i];
-    Q[i + (size_t)c * nr] = -neg[i];
+// Slicing of the paired operand [V | W] (nr rows, 2 x 64 contraction entries; V, W: nr x k with k <= 64, the unused
+// entries zero) straight from the two panels -- no packed copy.
+constexpr int PAIR_HALF = 64, PAIR_K = 2 * PAIR_HALF;
+__device__ __forceinline__ double pair_value(const double* __restrict__ V, long long ldv, const double* __restrict__ W, long long ldw,
+                                             int r, int kk, int k) {
+  const int c = kk & (PAIR_HALF - 1);
+  if (c >= k) return 0.0;
+  return kk < PAIR_HALF ? V[r + (long long)c * ldv] : W[r + (long long)c * ldw];
+}
+__global__ void k_rowmax_pair(const double* __restrict__ V, long long ldv, const double* __restrict__ W, long long ldw, int nr, int k,
+                              int* __restrict__ ex) {
+  __shared__ double sm[8][32];
+  const int r = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;  // 32 rows x 8 column groups
+  double mx = 0;
+  if (r < nr)
+    for (int kk = g; kk < PAIR_K; kk += 8) mx = fmax(mx, abs_or_inf(pair_value(V, ldv, W, ldw, r, kk, k)));
+  sm[g][threadIdx.x & 31] = mx;
+  __syncthreads();
+  if (g == 0 && r < nr) {
+    for (int w = 1; w < 8; ++w) mx = fmax(mx, sm[w][threadIdx.x]);
+    int e = 0;
+    if (mx > 0 && isfinite(mx)) frexp(mx, &e);
+    ex[r] = isfinite(mx) ? e : EX_NONFINITE;
+  }
+}
+__global__ void k_slice_pair(const double* __restrict__ V, long long ldv, const double* __restrict__ W, long long ldw, int nr, int k,
+                             const int* __restrict__ ex, int S, int64_t Rp, int8_t* __restrict__ Q) {
+  __shared__ int8_t tile[MAXS][32][33];
+  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  for (int kl = threadIdx.y; kl < 32; kl += blockDim.y) {
+    const int r = r0 + threadIdx.x, kk = k0 + kl;
+    int8_t q[MAXS];
+#pragma unroll
+    for (int t = 0; t < MAXS; ++t) q[t] = 0;
+    if (r < nr) slice_value(pair_value(V, ldv, W, ldw, r, kk, k), ex[r], S, q);
+    for (int t = 0; t < S; ++t) tile[t][threadIdx.x][kl] = q[t];
+  }
+  __syncthreads();
+  for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+    const int r = r0 + rr;
+    if (r < Rp)
+      for (int t = 0; t < S; ++t) Q[((int64_t)t * Rp + r) * PAIR_K + k0 + threadIdx.x] = tile[t][rr][threadIdx.x];
   }
 }
 // small trailing blocks: one thread per lower-triangle entry
@@ -578,13 +645,23 @@ void ozaki_syr2k_lower_sub(const double* V, int64_t ldv, const double* W, int64_
     RS_LAUNCH(oz::k_syr2k_small, grid, block, 0, V, (long long)ldv, W, (long long)ldw, (int)nr, k, C, (long long)ldc);
     return;
   }
-  DevBuf<double> P((size_t)nr * 2 * k), Q((size_t)nr * 2 * k);
-  dim3 grid((unsigned)std::min<int64_t>(cdiv(nr, 256), 64), (unsigned)(2 * k));
-  RS_LAUNCH(oz::k_pack_syr2k, grid, 256, 0, V, (long long)ldv, W, (long long)ldw, (int)nr, k, P.p, Q.p);
-  oz::Operand a, b;
-  oz::slice_operand(P.p, nr, nr, 2 * k, /*contig=*/false, ozaki_slices(), a);
-  oz::slice_operand(Q.p, nr, nr, 2 * k, /*contig=*/false, ozaki_slices(), b);
-  oz::run(a, b, C, nr, nr, ldc, /*lower_only=*/true, /*accumulate=*/true);
+  RS_REQUIRE(k <= oz::PAIR_HALF, "syr2k: panel wider than 64 columns");
+  // [V | W] sliced ONCE: the second factor [W | V] is the same operand with its k-blocks rotated by two (64 entries),
+  // and the minus sign goes into the epilogue
+  oz::Operand a;
+  a.R = nr; a.K = oz::PAIR_K; a.S = ozaki_slices();
+  a.Rp = (nr + oz::ROWPAD - 1) / oz::ROWPAD * oz::ROWPAD;
+  a.Kp = oz::PAIR_K;
+  a.Q.alloc((size_t)a.S * a.Rp * a.Kp);
+  a.ex.alloc(a.Rp);
+  {
+    Phase ph("ozaki_slice");
+    RS_CUDA(cudaMemsetAsync(a.ex.p, 0, sizeof(int) * a.Rp, ctx().stream));
+    RS_LAUNCH(oz::k_rowmax_pair, (unsigned)cdiv(nr, 32), 256, 0, V, (long long)ldv, W, (long long)ldw, (int)nr, k, a.ex.p);
+    dim3 grid(oz::PAIR_K / 32, (unsigned)(a.Rp / 32)), block(32, 8);
+    RS_LAUNCH(oz::k_slice_pair, grid, block, 0, V, (long long)ldv, W, (long long)ldw, (int)nr, k, a.ex.p, a.S, a.Rp, a.Q.p);
+  }
+  oz::run(a, a, C, nr, nr, ldc, /*lower_only=*/true, /*accumulate=*/true, /*b_kshift=*/oz::PAIR_HALF / oz::BK, /*negate=*/true);
 }
 void ozaki_gemm_tn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K) {
   oz::Operand a, b;
