@@ -31,7 +31,7 @@ extern "C" {
 #define RSOPTSC_STOP_EPSILON 3
 
 /* status returned when the caller's progress callback asked to stop (rsoptsc_set_progress) */
-#define RSOPTSC_STATUS_INTERRUPTED 7
+#define RSOPTSC_STATUS_INTERRUPTED 9
 
 /* ---- lifecycle ------------------------------------------------------------------- */
 int rsoptsc_abi_version(void);

@@ -108,7 +108,7 @@ def set_progress(fn):
     """Install (fn) or remove (None) the progress / interrupt hook of the C ABI (rsoptsc_set_progress).
     fn(stage, iter, value) is called once per computeM iteration (stage 0, value = Err[iter, 1], the number
     the reference prints at R/SimilarityM.R:191) and at every NMF stop check (stage 1); a true return value
-    aborts the running call with RsoptscError (status 7, the R shim's R_CheckUserInterrupt)."""
+    aborts the running call with RsoptscError (status 9, the R shim's R_CheckUserInterrupt)."""
     global _progress_keepalive
     lib = _lib.init()
     if fn is None:

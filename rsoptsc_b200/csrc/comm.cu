@@ -120,6 +120,44 @@ void comm_allgather_cols(double* d_base, int64_t rows, const std::vector<int64_t
   g_comm.collectives++;
 }
 
+// ---- gather of a column panel whose ROWS are owned cyclically in groups (sharded trailing update of sytrd_mg) ----
+// rows of rank q below x: full cycles, the full groups of the last cycle, the partial group
+__host__ __device__ inline long long cyc_rows_below(long long x, int group, int P, int q) {
+  const long long G = x / group, cyc = G / P, rem = G % P;
+  return cyc * group + (rem > q ? group : 0) + (rem == q ? x % group : 0);
+}
+// dir 0: pack the rows of `rank` into buf[(idx) + c * lmax]; dir 1: unpack the rows of every OTHER rank from
+// buf[q * lmax * ncols + idx + c * lmax]
+__global__ void k_cyc_panel(double* __restrict__ A, long long lda, int n, int r0, int ncols, int group, int P, int rank, int lmax,
+                            double* __restrict__ buf, int dir) {
+  const int c = blockIdx.y;
+  for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int q = (i / group) % P;
+    if ((dir == 0) != (q == rank)) continue;
+    const long long idx = cyc_rows_below(i, group, P, q) - cyc_rows_below(r0, group, P, q);
+    double* a = A + i + (long long)(r0 + c) * lda;
+    double* b = buf + (dir == 0 ? 0 : (size_t)q * lmax * ncols) + idx + (size_t)c * lmax;
+    if (dir == 0) *b = *a; else *a = *b;
+  }
+}
+void comm_gather_cyclic_rows(double* d_A, int64_t lda, int64_t n, int64_t r0, int ncols, int group) {
+  if (!sharded() || ncols < 1 || r0 >= n) return;
+  Phase ph("panel_gather");
+  cudaStream_t s = ctx().stream;
+  const int P = g_comm.nranks;
+  long long lmax = 0;
+  for (int q = 0; q < P; ++q) lmax = std::max(lmax, cyc_rows_below(n, group, P, q) - cyc_rows_below(r0, group, P, q));
+  if (lmax < 1) return;
+  DevBuf<double> buf((size_t)P * lmax * ncols);
+  double* mine = buf.p + (size_t)g_comm.rank * lmax * ncols;
+  dim3 grid((unsigned)std::min<int64_t>(cdiv(n - r0, 256), 128), (unsigned)ncols);
+  RS_LAUNCH(k_cyc_panel, grid, 256, 0, d_A, (long long)lda, (int)n, (int)r0, ncols, group, P, g_comm.rank, (int)lmax, mine, 0);
+  RS_NCCL(ncclAllGather(mine, buf.p, (size_t)lmax * ncols, ncclDouble, nc(), s));
+  RS_LAUNCH(k_cyc_panel, grid, 256, 0, d_A, (long long)lda, (int)n, (int)r0, ncols, group, P, g_comm.rank, (int)lmax, buf.p, 1);
+  g_comm.collectives++;
+  g_comm.collective_bytes += 8.0 * (double)lmax * ncols * (P - 1);
+}
+
 bool comm_ensure_xchg(size_t doubles) {
   if (!sharded()) return false;
   if (g_comm.xchg_doubles >= doubles) return g_comm.p2p;

@@ -45,6 +45,9 @@ void comm_barrier();
 // Column-major matrix with `rows` rows replicated on every rank; rank q has just produced columns
 // [begin[q], begin[q+1]).  On return every rank holds every column.
 void comm_allgather_cols(double* d_base, int64_t rows, const std::vector<int64_t>& begin);
+// Column panel [r0, r0 + ncols) x rows [r0, n) of a replicated column-major matrix whose rows are CURRENT only on
+// their owner -- row i belongs to rank (i / group) mod nranks -- made current on every rank (pack, all-gather, unpack).
+void comm_gather_cyclic_rows(double* d_A, int64_t lda, int64_t n, int64_t r0, int ncols, int group);
 // (re)allocate the peer-mapped exchange regions (collective).  Returns false when CUDA IPC is not
 // available between the ranks: the callers then keep the tridiagonalisation replicated.
 bool comm_ensure_xchg(size_t doubles);

@@ -143,9 +143,18 @@ static int64_t native_min_n() {
 }
 
 // trailing update of the tridiagonalisation on the library's own GEMM (tcgen05 split-integer kernel, gemm.cu)
+// user: null = update the whole block; else int[2] {nranks, rank}: this rank's 128-row groups only (sytrd_mg.cu)
 void sytrd_trailing_update(const double* V, long long ldv, const double* W, long long ldw, long long nr, int k, double* C,
-                           long long ldc) {
-  syr2k_lower_sub(V, ldv, W, ldw, nr, k, C, ldc);
+                           long long ldc, long long r0, void* user) {
+  const int* sh = static_cast<const int*>(user);
+  syr2k_lower_sub(V, ldv, W, ldw, nr, k, C, ldc, r0, sh ? sh[0] : 1, sh ? sh[1] : 0);
+  if (sh) {
+    // sharded update: every row of the trailing block is current on its owner only.  The next panel's kernel reads
+    // its 64 columns in full on every rank, so those columns are gathered (the diagonal entry of the last row too)
+    double* A = C - r0 - r0 * ldc;
+    const long long n = r0 + nr;
+    comm_gather_cyclic_rows(A, ldc, n, r0, (int)std::min<long long>(sytrd::NB, nr), 2 * sytrd::TILE);
+  }
 }
 
 static void sym_eig_native(double* d_A, int64_t n, double* d_lam, double keep_above = -1.0e300, bool collective = false) {

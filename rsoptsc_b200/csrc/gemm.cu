@@ -22,7 +22,8 @@ void ozaki_gemm_tn(const double* A, const double* B, double* C, int64_t M, int64
 void ozaki_gemm_nt_ld(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M,
                       int64_t N, int64_t K);
 
-void ozaki_syr2k_lower_sub(const double* V, int64_t ldv, const double* W, int64_t ldw, int64_t nr, int k, double* C, int64_t ldc);
+void ozaki_syr2k_lower_sub(const double* V, int64_t ldv, const double* W, int64_t ldw, int64_t nr, int k, double* C, int64_t ldc,
+                           int64_t r0, int nranks, int rank);
 
 static int g_backend = -1;  // 0 cublas, 1 ozaki
 int gemm_backend() {
@@ -104,9 +105,10 @@ void gemm_nt_ld(const double* A, int64_t lda, const double* B, int64_t ldb, doub
   RS_CUBLAS(cublasDgemm(ctx().cublas, CUBLAS_OP_N, CUBLAS_OP_T, (int)M, (int)N, (int)K, &one, A, (int)lda, B, (int)ldb,
                         &zero, C, (int)ldc));
 }
-void syr2k_lower_sub(const double* V, int64_t ldv, const double* W, int64_t ldw, int64_t nr, int k, double* C, int64_t ldc) {
+void syr2k_lower_sub(const double* V, int64_t ldv, const double* W, int64_t ldw, int64_t nr, int k, double* C, int64_t ldc,
+                     int64_t r0, int nranks, int rank) {
   Phase ph("sytrd_syr2k");
-  if (gemm_backend() != 0 && nr <= 65535) return ozaki_syr2k_lower_sub(V, ldv, W, ldw, nr, k, C, ldc);
+  if (gemm_backend() != 0 && nr <= 65535) return ozaki_syr2k_lower_sub(V, ldv, W, ldw, nr, k, C, ldc, r0, nranks, rank);
   const double mone = -1.0, one = 1.0;
   RS_CUBLAS(cublasDsyr2k(ctx().cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)nr, k, &mone, V, (int)ldv, W, (int)ldw, &one, C,
                          (int)ldc));

@@ -28,6 +28,9 @@ void gemm_nt_ld(const double* A, int64_t lda, const double* B, int64_t ldb, doub
                 int64_t K);
 // C (M x N) = A^T * B, A: K x M, B: K x N
 void gemm_tn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K);
-// C (nr x nr, lower triangle) -= V W^T + W V^T, V and W nr x k (trailing update of the tridiagonalisation)
-void syr2k_lower_sub(const double* V, int64_t ldv, const double* W, int64_t ldw, int64_t nr, int k, double* C, int64_t ldc);
+// C (nr x nr, lower triangle) -= V W^T + W V^T, V and W nr x k (trailing update of the tridiagonalisation).
+// nranks > 1: only the 128-row groups (absolute rows, the block starts at row r0) of rank `rank` and the first 64
+// columns are updated -- the rows the fused multi-GPU tridiagonalisation lets that rank read (sytrd_mg.cuh).
+void syr2k_lower_sub(const double* V, int64_t ldv, const double* W, int64_t ldw, int64_t nr, int k, double* C, int64_t ldc,
+                     int64_t r0 = 0, int nranks = 1, int rank = 0);
 }  // namespace rs

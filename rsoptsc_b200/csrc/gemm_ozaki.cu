@@ -470,8 +470,10 @@ static CUtensorMap make_map(const Operand& op, int depth) {
   return m;
 }
 
+// tile_rows (optional): keep only the tiles whose tile row i has tile_rows[i] != 0 (the sharded trailing update:
+// a rank's own 128-row groups)
 static void run(const Operand& a, const Operand& b, double* C, int64_t M, int64_t N, int64_t ldc, bool lower_only,
-                bool accumulate, int b_kshift = 0, bool negate = false) {
+                bool accumulate, int b_kshift = 0, bool negate = false, const std::vector<char>* tile_rows = nullptr) {
   RS_REQUIRE(a.Kp == b.Kp && a.S == b.S, "ozaki: operand mismatch");
   const int tm = (int)cdiv(M, BM), tn = (int)cdiv(N, BN);
   // Rasterise in G x G super-blocks: the ~148 tiles in flight then share G panels of A rows and G
@@ -483,7 +485,9 @@ static void run(const Operand& a, const Operand& b, double* C, int64_t M, int64_
     for (int i0 = 0; i0 < tm; i0 += G)
       for (int j = j0; j < std::min(tn, j0 + G); ++j)
         for (int i = i0; i < std::min(tm, i0 + G); ++i)
-          if (!lower_only || (int64_t)j * BN <= (int64_t)i * BM + BM - 1) tiles.push_back(make_int2(i, j));
+          if ((!lower_only || (int64_t)j * BN <= (int64_t)i * BM + BM - 1) && (!tile_rows || (*tile_rows)[i]))
+            tiles.push_back(make_int2(i, j));
+  if (tiles.empty()) return;
   DevBuf<int2> d_tiles(tiles.size());
   RS_CUDA(cudaMemcpyAsync(d_tiles.p, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, ctx().stream));
   Params P;
@@ -586,19 +590,21 @@ namespace oz {
 // Slicing of the paired operand [V | W] (nr rows, 2 x 64 contraction entries; V, W: nr x k with k <= 64, the unused
 // entries zero) straight from the two panels -- no packed copy.
 constexpr int PAIR_HALF = 64, PAIR_K = 2 * PAIR_HALF;
+// operand row r = matrix row r - lead: the first `lead` operand rows are zero (they align the operand with absolute
+// 128-row groups; their outputs get +0)
 __device__ __forceinline__ double pair_value(const double* __restrict__ V, long long ldv, const double* __restrict__ W, long long ldw,
-                                             int r, int kk, int k) {
+                                             int r, int kk, int k, int lead) {
   const int c = kk & (PAIR_HALF - 1);
-  if (c >= k) return 0.0;
-  return kk < PAIR_HALF ? V[r + (long long)c * ldv] : W[r + (long long)c * ldw];
+  if (c >= k || r < lead) return 0.0;
+  return kk < PAIR_HALF ? V[(r - lead) + (long long)c * ldv] : W[(r - lead) + (long long)c * ldw];
 }
 __global__ void k_rowmax_pair(const double* __restrict__ V, long long ldv, const double* __restrict__ W, long long ldw, int nr, int k,
-                              int* __restrict__ ex) {
+                              int lead, int* __restrict__ ex) {
   __shared__ double sm[8][32];
   const int r = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;  // 32 rows x 8 column groups
   double mx = 0;
   if (r < nr)
-    for (int kk = g; kk < PAIR_K; kk += 8) mx = fmax(mx, abs_or_inf(pair_value(V, ldv, W, ldw, r, kk, k)));
+    for (int kk = g; kk < PAIR_K; kk += 8) mx = fmax(mx, abs_or_inf(pair_value(V, ldv, W, ldw, r, kk, k, lead)));
   sm[g][threadIdx.x & 31] = mx;
   __syncthreads();
   if (g == 0 && r < nr) {
@@ -609,7 +615,7 @@ __global__ void k_rowmax_pair(const double* __restrict__ V, long long ldv, const
   }
 }
 __global__ void k_slice_pair(const double* __restrict__ V, long long ldv, const double* __restrict__ W, long long ldw, int nr, int k,
-                             const int* __restrict__ ex, int S, int64_t Rp, int8_t* __restrict__ Q) {
+                             int lead, const int* __restrict__ ex, int S, int64_t Rp, int8_t* __restrict__ Q) {
   __shared__ int8_t tile[MAXS][32][33];
   const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
   for (int kl = threadIdx.y; kl < 32; kl += blockDim.y) {
@@ -617,7 +623,7 @@ __global__ void k_slice_pair(const double* __restrict__ V, long long ldv, const 
     int8_t q[MAXS];
 #pragma unroll
     for (int t = 0; t < MAXS; ++t) q[t] = 0;
-    if (r < nr) slice_value(pair_value(V, ldv, W, ldw, r, kk, k), ex[r], S, q);
+    if (r < nr) slice_value(pair_value(V, ldv, W, ldw, r, kk, k, lead), ex[r], S, q);
     for (int t = 0; t < S; ++t) tile[t][threadIdx.x][kl] = q[t];
   }
   __syncthreads();
@@ -638,7 +644,11 @@ __global__ void k_syr2k_small(const double* __restrict__ V, long long ldv, const
   C[i + (long long)j * ldc] -= acc;
 }
 }  // namespace oz
-void ozaki_syr2k_lower_sub(const double* V, int64_t ldv, const double* W, int64_t ldw, int64_t nr, int k, double* C, int64_t ldc) {
+// r0: absolute index of the first row of the trailing block; nranks > 1: update only the 128-row groups of rank
+// `rank` (group g of absolute rows [128 g, 128 g + 128) belongs to rank g mod nranks, the ownership of
+// sytrd_mg.cuh).  The caller gathers the next panel's columns afterwards (comm_gather_cyclic_rows).
+void ozaki_syr2k_lower_sub(const double* V, int64_t ldv, const double* W, int64_t ldw, int64_t nr, int k, double* C, int64_t ldc,
+                           int64_t r0, int nranks, int rank) {
   if (nr < 1 || k < 1) return;
   if (nr < 384) {
     dim3 grid((unsigned)cdiv(nr, 32), (unsigned)cdiv(nr, 8)), block(32, 8);
@@ -646,22 +656,33 @@ void ozaki_syr2k_lower_sub(const double* V, int64_t ldv, const double* W, int64_
     return;
   }
   RS_REQUIRE(k <= oz::PAIR_HALF, "syr2k: panel wider than 64 columns");
+  // sharded: the tile grid starts at the absolute multiple of 128 at or below r0 (lead = 0 or 64 zero rows)
+  const int lead = nranks > 1 ? (int)(r0 % oz::BM) : 0;
+  const int64_t rows = nr + lead;
   // [V | W] sliced ONCE: the second factor [W | V] is the same operand with its k-blocks rotated by two (64 entries),
   // and the minus sign goes into the epilogue
   oz::Operand a;
-  a.R = nr; a.K = oz::PAIR_K; a.S = ozaki_slices();
-  a.Rp = (nr + oz::ROWPAD - 1) / oz::ROWPAD * oz::ROWPAD;
+  a.R = rows; a.K = oz::PAIR_K; a.S = ozaki_slices();
+  a.Rp = (rows + oz::ROWPAD - 1) / oz::ROWPAD * oz::ROWPAD;
   a.Kp = oz::PAIR_K;
   a.Q.alloc((size_t)a.S * a.Rp * a.Kp);
   a.ex.alloc(a.Rp);
   {
     Phase ph("ozaki_slice");
     RS_CUDA(cudaMemsetAsync(a.ex.p, 0, sizeof(int) * a.Rp, ctx().stream));
-    RS_LAUNCH(oz::k_rowmax_pair, (unsigned)cdiv(nr, 32), 256, 0, V, (long long)ldv, W, (long long)ldw, (int)nr, k, a.ex.p);
+    RS_LAUNCH(oz::k_rowmax_pair, (unsigned)cdiv(rows, 32), 256, 0, V, (long long)ldv, W, (long long)ldw, (int)rows, k, lead, a.ex.p);
     dim3 grid(oz::PAIR_K / 32, (unsigned)(a.Rp / 32)), block(32, 8);
-    RS_LAUNCH(oz::k_slice_pair, grid, block, 0, V, (long long)ldv, W, (long long)ldw, (int)nr, k, a.ex.p, a.S, a.Rp, a.Q.p);
+    RS_LAUNCH(oz::k_slice_pair, grid, block, 0, V, (long long)ldv, W, (long long)ldw, (int)rows, k, lead, a.ex.p, a.S, a.Rp, a.Q.p);
   }
-  oz::run(a, a, C, nr, nr, ldc, /*lower_only=*/true, /*accumulate=*/true, /*b_kshift=*/oz::PAIR_HALF / oz::BK, /*negate=*/true);
+  std::vector<char> mine;
+  if (nranks > 1) {
+    const int64_t g0 = (r0 - lead) / oz::BM;  // absolute group of tile row 0
+    mine.resize((size_t)cdiv(rows, oz::BM));
+    for (size_t i = 0; i < mine.size(); ++i) mine[i] = ((g0 + (int64_t)i) % nranks) == rank;
+  }
+  double* C0 = C - lead - (int64_t)lead * ldc;  // absolute (r0 - lead, r0 - lead): inside the matrix, never written there
+  oz::run(a, a, C0, rows, rows, ldc, /*lower_only=*/true, /*accumulate=*/true, /*b_kshift=*/oz::PAIR_HALF / oz::BK, /*negate=*/true,
+          nranks > 1 ? &mine : nullptr);
 }
 void ozaki_gemm_tn(const double* A, const double* B, double* C, int64_t M, int64_t N, int64_t K) {
   oz::Operand a, b;

@@ -639,13 +639,16 @@ struct Hooks {  // optional instrumentation around every panel launch (phase tim
   void* user = nullptr;
   // trailing update C(lower, nr x nr) -= V W^T + W V^T on the caller's own GEMM (the library passes its tcgen05
   // split-integer kernel, gemm_ozaki.cu); null: cublasDsyr2k (stand-alone probes)
+  // r0: absolute index of the first row / column of the trailing block (the multi-GPU path shards the update by
+  // absolute 128-row groups); syr2k_user: the caller's cookie
   void (*syr2k)(const double* V, long long ldv, const double* W, long long ldw, long long nr, int k, double* C,
-                long long ldc) = nullptr;
+                long long ldc, long long r0, void* user) = nullptr;
+  void* syr2k_user = nullptr;
 };
 inline cudaError_t trailing_update(cublasHandle_t blas, const Hooks* hooks, const double* V, long long ldv, const double* W,
-                                   long long ldw, long long nr, int k, double* C, long long ldc) {
+                                   long long ldw, long long nr, int k, double* C, long long ldc, long long r0) {
   if (hooks && hooks->syr2k) {
-    hooks->syr2k(V, ldv, W, ldw, nr, k, C, ldc);
+    hooks->syr2k(V, ldv, W, ldw, nr, k, C, ldc, r0, hooks->syr2k_user);
     return cudaSuccess;
   }
   const double mone = -1.0, one = 1.0;
@@ -697,7 +700,7 @@ inline cudaError_t run(cublasHandle_t blas, cudaStream_t stream, double* A, int6
     if (launches) ++*launches;
     const int64_t r0 = j0 + pw, nr = n - r0;  // trailing block
     if (nr > 0) {
-      st = trailing_update(blas, hooks, A + r0 + j0 * lda, lda, P.W + r0, n, nr, pw, A + r0 + r0 * lda, lda);
+      st = trailing_update(blas, hooks, A + r0 + j0 * lda, lda, P.W + r0, n, nr, pw, A + r0 + r0 * lda, lda, r0);
       if (st != cudaSuccess) return st;
     }
   }

@@ -3,12 +3,13 @@
 #include "sytrd_mg.cuh"
 
 #include "comm.h"
+#include "gemm.h"
 #include "internal.h"
 
 namespace rs {
 
 void sytrd_trailing_update(const double* V, long long ldv, const double* W, long long ldw, long long nr, int k, double* C,
-                           long long ldc);  // eig.cu
+                           long long ldc, long long r0, void* user);  // eig.cu
 
 static int64_t mg_min_n() {
   // the exchange adds ~3 us per column; the product phase of a column takes 14.5 us (n / 7,954)^2 on one GPU and
@@ -45,10 +46,15 @@ void sytrd_mg_run(double* d_A, int64_t n, double* d_d, double* d_e, double* d_ta
     comm_barrier();  // nobody writes into a region before its owner has cleared it
   }
   DevBuf<double> work(sytrd::workspace_doubles(n));
+  DevBuf<char> tabbuf(sytrd::mg_tab_bytes(n));
   sytrd::Hooks hooks;
   Phase* panel_phase = nullptr;
   hooks.user = &panel_phase;
   hooks.syr2k = sytrd_trailing_update;
+  // RSOPTSC_SYR2K_SHARD=0 keeps the trailing update replicated (every rank updates everything; tests compare)
+  static const bool shard_update = !(getenv("RSOPTSC_SYR2K_SHARD") && getenv("RSOPTSC_SYR2K_SHARD")[0] == '0');
+  int shard_info[2] = {cm.nranks, cm.rank};
+  hooks.syr2k_user = (shard_update && gemm_backend() != 0) ? shard_info : nullptr;
   hooks.before = [](void* u, double bytes) {
     add_counter("sytrd_panel_bytes", bytes);
     *static_cast<Phase**>(u) = new Phase("sytrd_panel");
@@ -59,7 +65,7 @@ void sytrd_mg_run(double* d_A, int64_t n, double* d_d, double* d_e, double* d_ta
   };
   int64_t launches = 0;
   const int grid = std::min(c.sm_count, sytrd::MAX_GRID);  // identical on every rank (arrival targets count CTAs)
-  RS_CUDA(sytrd::run_mg(c.cublas, c.stream, d_A, n, n, d_d, d_e, d_tau, work.p, cm.nranks, cm.rank, cm.xchg, epoch, grid,
+  RS_CUDA(sytrd::run_mg(c.cublas, c.stream, d_A, n, n, d_d, d_e, d_tau, work.p, tabbuf.p, cm.nranks, cm.rank, cm.xchg, epoch, grid,
                         &launches, &hooks));
   g_launches.fetch_add(launches, std::memory_order_relaxed);
   cm.collectives += (n + sytrd::NB - 1) / sytrd::NB;  // one fused compute + exchange kernel per panel

@@ -4,10 +4,13 @@
 // panel instead of two NCCL calls per column (a4: the symmetric eigensolver behind the SVT of
 // R/SimilarityM.R:142-155 is 85 % of a 50,000-cell run, and this product is 70 % of it).
 //
-//   * The (replicated) trailing matrix is cut by BLOCK ROWS of the lower triangle into P parts of equal
-//     area; rank r streams only its part (1/P of the 4 n'^2 bytes per column) with the strip / run / butterfly
-//     scheme of the single-GPU kernel, on its own unit map.  The panel dot products W^T v, V^T v are dealt
-//     round-robin.
+//   * The trailing matrix is owned by 128-ROW GROUPS dealt cyclically: block row I (64 rows, absolute index)
+//     belongs to rank (I / 2) mod P for the whole factorisation.  Rank r streams only its block rows (1/P of the
+//     4 n'^2 bytes per column, balanced to within one group for every column) with the strip / run / butterfly
+//     scheme of the single-GPU kernel on its own unit map (three small lookup tables, MgTab).  Because ownership
+//     never moves, a rank only ever reads its own rows of the trailing matrix -- so the rank-2NB trailing update
+//     between panels is sharded as well: every rank updates its own 128-row groups and nothing else; the only
+//     data every rank reads in full, the next panel's 64 columns, is all-gathered once per panel (NCCL, <= 20 MB).  The panel dot products W^T v, V^T v are dealt round-robin.
 //   * After its product phase a rank reduces its OWN partial sums to one n'-vector (rows it touched, zeros
 //     elsewhere) and writes that vector -- plus its share of W^T v, V^T v and v^T A v -- straight into the
 //     exchange region of every rank with NVLink stores.  Every value travels as one 16-byte flag-with-data
@@ -17,10 +20,11 @@
 //     counters cost ~14 us per column at 7,954 rows, more than the product phase it saved on 2 GPUs).
 //     Buffers alternate with the column parity: a rank can run at most one column ahead of a peer.
 //   * The row phase (w, the final W column, the update of column j+1) runs replicated on bitwise identical
-//     sums, so the panel, the reflectors and d/e/tau stay identical on all ranks and the rank-2NB trailing
-//     update needs no communication at all.
+//     sums, so the panel, the reflectors and d/e/tau stay identical on all ranks.
 // Per column: two local grid barriers (as before) + one cross-GPU exchange.
 #pragma once
+#include <vector>
+
 #include "sytrd_kernel.cuh"
 
 namespace rs {
@@ -30,8 +34,21 @@ constexpr int MG_MAX_RANKS = 8;  // == TPR: one lane of a row group per rank in 
 constexpr int XCH_HDR = 32;      // doubles at the head of an exchange region (reserved)
 static_assert(MG_MAX_RANKS <= TPR, "row phase reads one rank per lane of a row group");
 
+// Ownership tables of one rank (device, built once per factorisation by run_mg):
+//   ownI[l]   absolute block row of the rank's l-th block row, ascending (l < nl)
+//   pref[l]   sum over t < l of SPT (ownI[t] + 1): strips of the rows before l counted from column block 0
+//   lfirst[I] first l with ownI[l] >= I (nl when there is none), I = 0 .. mB
+struct MgTab {
+  const int* ownI;
+  const long long* pref;
+  const int* lfirst;
+  int nl;
+};
+__host__ __device__ inline int mg_owner_of_block_row(int I, int nranks) { return (I >> 1) % nranks; }
+
 struct MgParams {
   Params b;
+  MgTab tab;
   int nranks, rank;
   double* xch[MG_MAX_RANKS];  // exchange region of every rank as mapped in this process
   long long xlen;             // packets per exchanged vector: y (n) | W^T v (NB) | V^T v (NB) | v^T A v | pad
@@ -67,37 +84,28 @@ __device__ __forceinline__ double ll_load(const uint4* slot, unsigned flag) {
   return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
 
-// Unit map of one rank for one column: its block rows [b0, b1) of the trailing triangle (relative to Bmin),
-// enumerated along block rows exactly like the single-GPU map (absolute unit = local + u0), then its share of
-// the panel dot-product units (global unit r = t * nranks + rank).
+// Unit map of one rank for one column j: its block rows at or below Bmin = (j + 1) / 64 (local rows l0 .. nl-1 of
+// MgTab), enumerated along block rows like the single-GPU map -- local row l holds SPT (ownI[l] - Bmin + 1) strips,
+// the first at unit F(l) -- then its share of the panel dot-product units (global unit r = t * nranks + rank).
 struct MgMap {
-  int Bmin, mt, nch, b0, b1;
-  long long u0, strips, ndot, total, nw;
-  __device__ __forceinline__ static long long first_of_row(int b) { return (long long)SPT * b * (b + 1) / 2; }
+  int Bmin, mt, nch, l0, nl, bf;
+  long long pref0, strips, ndot, total, nw;
+  __device__ __forceinline__ long long F(const MgTab& t, int l) const {
+    return __ldg(t.pref + l) - pref0 - (long long)SPT * Bmin * (l - l0);
+  }
   __device__ __forceinline__ long long start(long long g) const { return (g * total + nw - 1) / nw; }
   __device__ __forceinline__ long long owner(long long u) const { return u * nw / total; }
 };
-__host__ __device__ inline int mg_brow(int q, int nranks, int mt) {
-  if (q <= 0) return 0;
-  if (q >= nranks) return mt;
-  const long long S = (long long)SPT * mt * (mt + 1) / 2;
-  const long long t = (S * q + nranks - 1) / nranks;
-  int b = (int)ceil((sqrt(1.0 + 8.0 * (double)t / SPT) - 1.0) * 0.5);
-  if (b < 0) b = 0;
-  if (b > mt) b = mt;
-  while (b < mt && (long long)SPT * b * (b + 1) / 2 < t) ++b;
-  while (b > 0 && (long long)SPT * (b - 1) * b / 2 >= t) --b;
-  return b;
-}
-__device__ __forceinline__ MgMap mg_map(int nranks, int rank, int j, int jj, int n, int mB, long long nwarps) {
+__device__ __forceinline__ MgMap mg_map(const MgTab& tab, int nranks, int rank, int j, int jj, int n, int mB, long long nwarps) {
   MgMap m;
   m.Bmin = (j + 1) / TILE;
   m.mt = mB - m.Bmin;
   m.nch = (n - j - 1 + DOT_CHUNK - 1) / DOT_CHUNK;
-  m.b0 = mg_brow(rank, nranks, m.mt);
-  m.b1 = mg_brow(rank + 1, nranks, m.mt);
-  m.u0 = MgMap::first_of_row(m.b0);
-  m.strips = MgMap::first_of_row(m.b1) - m.u0;
+  m.nl = tab.nl;
+  m.l0 = m.Bmin <= mB ? __ldg(tab.lfirst + m.Bmin) : tab.nl;
+  m.pref0 = __ldg(tab.pref + m.l0);
+  m.bf = m.l0 < m.nl ? __ldg(tab.ownI + m.l0) - m.Bmin : 0;
+  m.strips = m.F(tab, m.nl);
   const long long tdot = 2LL * jj * m.nch;
   m.ndot = tdot > rank ? (tdot - rank + nranks - 1) / nranks : 0;
   m.total = m.strips + m.ndot;
@@ -105,26 +113,28 @@ __device__ __forceinline__ MgMap mg_map(int nranks, int rank, int j, int jj, int
   if (m.nw < 1) m.nw = 1;  // empty share: start(0) = start(1) = 0
   return m;
 }
-// block row (relative to Bmin) of absolute strip unit u
-__device__ __forceinline__ int mg_row_of(long long u) {
-  int b = (int)floor((sqrt(1.0 + 8.0 * (double)u / SPT) - 1.0) * 0.5);
-  if (b < 0) b = 0;
-  while (b > 0 && MgMap::first_of_row(b) > u) --b;
-  while (MgMap::first_of_row(b + 1) <= u) ++b;
-  return b;
+// local row l (l0 <= l < nl) of strip unit u < strips: F(l) <= u < F(l + 1).  The rows of a rank advance by 2 nranks
+// block rows per pair, so F is close to a quadratic in l - l0: solve it for the first guess, settle with the table.
+__device__ __forceinline__ int mg_local_row(const MgTab& tab, const MgMap& m, int nranks, long long u) {
+  const double b1 = (double)m.bf + 1.0;
+  int l = m.l0 + (int)((sqrt(b1 * b1 + 2.0 * nranks * (double)u / SPT) - b1) / nranks);
+  if (l > m.nl - 1) l = m.nl - 1;
+  if (l < m.l0) l = m.l0;
+  while (l > m.l0 && m.F(tab, l) > u) --l;
+  while (l + 1 < m.nl && m.F(tab, l + 1) <= u) ++l;
+  return l;
 }
 
-__device__ __forceinline__ long long mg_stage_next_strip(const Params& P, const MgMap& um, long long gwarp, int lane, double* sbuf,
-                                                         int jnext) {
+__device__ __forceinline__ long long mg_stage_next_strip(const Params& P, const MgTab& tab, const MgMap& um, int nranks,
+                                                         long long gwarp, int lane, double* sbuf, int jnext) {
   if (!RS_SYTRD_STAGE || jnext + 1 >= P.n) return -1;
   if (um.total < 1 || gwarp >= um.nw) return -1;
   const long long u = um.start(gwarp);
   if (u >= um.strips || u >= um.start(gwarp + 1)) return -1;
   const int n = P.n;
-  const long long ua = u + um.u0;
-  const int b = mg_row_of(ua);
-  const int k = (int)(ua - MgMap::first_of_row(b));
-  const int I = um.Bmin + b;
+  const int l = mg_local_row(tab, um, nranks, u);
+  const int k = (int)(u - um.F(tab, l));
+  const int I = __ldg(tab.ownI + l);
   const int cbase = um.Bmin * TILE + k * SW;
   const int r0 = I * TILE + lane, r1 = r0 + 32;
   const unsigned s0 = (unsigned)__cvta_generic_to_shared(sbuf + lane), s1 = (unsigned)__cvta_generic_to_shared(sbuf + lane + 32);
@@ -143,22 +153,23 @@ __device__ __forceinline__ long long mg_stage_next_strip(const Params& P, const 
 // This rank's share of y(i): its row partial sums (when row i lies in one of its block rows) and the column
 // partial sums of its block rows at or below row i.  All TPR lanes of the row group call; lane `sub` adds every
 // TPR-th partial.  Unreduced.
-__device__ __forceinline__ double mg_row_partial(const Params& P, const MgMap& um, int i, bool live, int sub) {
+__device__ __forceinline__ double mg_row_partial(const Params& P, const MgTab& tab, const MgMap& um, int i, bool live, int sub) {
   double acc = 0;
   if (live) {
     const int n = P.n;
-    const int Ii = i / TILE, b = Ii - um.Bmin;
+    const int Ii = i / TILE;
+    const int lge = __ldg(tab.lfirst + max(Ii, um.Bmin));  // first own block row at or below row i
     int nrow = 0;
     const double* rp = P.rowpart;
-    if (b >= um.b0 && b < um.b1) {
-      const long long s0 = MgMap::first_of_row(b) - um.u0;
+    if (lge < um.nl && __ldg(tab.ownI + lge) == Ii) {      // row i lies in one of this rank's block rows
+      const int b = Ii - um.Bmin;
+      const long long s0 = um.F(tab, lge);
       const int g0 = (int)um.owner(s0), g1 = (int)um.owner(s0 + (long long)SPT * (b + 1) - 1);
       nrow = g1 - g0 + 1;
-      rp = P.rowpart + (size_t)(g0 + b - um.b0) * TILE + (i - Ii * TILE);
+      rp = P.rowpart + (size_t)(g0 + lge - um.l0) * TILE + (i - Ii * TILE);
     }
-    const int Ilo = max(Ii, um.Bmin + um.b0), Ihi = um.Bmin + um.b1;
-    const int ncol = max(0, Ihi - Ilo);
-    const double* cp = P.colpart + ((long long)Ilo * n + i);
+    const int ncol = max(0, um.nl - lge);                  // column partials are stored by LOCAL block row
+    const double* cp = P.colpart + ((long long)lge * n + i);
     const int ntot = nrow + ncol;
     for (int k0 = sub; k0 < ntot; k0 += TPR * KB) {
       double t[KB];
@@ -182,6 +193,7 @@ static __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel_mg(MgParams Q
   extern __shared__ double s_stage[];         // THREADS/32 x STAGE_DOUBLES: staged first strips
 
   const Params& P = Q.b;
+  const MgTab& tab = Q.tab;
   const int NR = Q.nranks, rank = Q.rank;
   const long long xlen = Q.xlen;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -225,11 +237,11 @@ static __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel_mg(MgParams Q
     const unsigned flag = (Q.epoch << 16) | (unsigned)((j + 1) & 0xffff);
     const double* ab = P.abuf + (size_t)(j & 1) * n;
     double* abn = P.abuf + (size_t)((j + 1) & 1) * n;
-    const MgMap um = mg_map(NR, rank, j, jj, n, P.mB, nwarps);
+    const MgMap um = mg_map(tab, NR, rank, j, jj, n, P.mB, nwarps);
 
     cta_reduce2(ss, alpha_part, s_tmp);
     {
-      auto stage = [&]() { staged = mg_stage_next_strip(P, um, gwarp, lane, sbuf, j); };
+      auto stage = [&]() { staged = mg_stage_next_strip(P, tab, um, NR, gwarp, lane, sbuf, j); };
       grid_allreduce2(P.slots, nblocks, gen, ss, alpha_part, s_out, stage);  // #1 (local: the data is replicated)
     }
 
@@ -255,8 +267,9 @@ static __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel_mg(MgParams Q
       long long u = um.start(gwarp);
       const long long uend = um.start(gwarp + 1);
       if (u < um.strips) {
-        int b = mg_row_of(u + um.u0);
-        int k = (int)(u + um.u0 - MgMap::first_of_row(b));
+        int l = mg_local_row(tab, um, NR, u);
+        int b = __ldg(tab.ownI + l) - Bmin;
+        int k = (int)(u - um.F(tab, l));
         double rs0 = 0, rs1 = 0, vi0 = 0, vi1 = 0;
         bool newrow = true;
         const long long send = uend < um.strips ? uend : um.strips;
@@ -325,19 +338,24 @@ static __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel_mg(MgParams Q
           if (col_writer(lane)) {
             const int cl = col_of_lane(lane);
             const int cg = cbase + cl;
-            if (cg < n) P.colpart[(size_t)I * n + cg] = cs;
+            if (cg < n) P.colpart[(size_t)l * n + cg] = cs;
             yv += cs * s_vj[warp][cl];
           }
           ++k;
           const bool endrow = (k == SPT * (b + 1));
           if (endrow || u + 1 == send) {
-            double* rp = P.rowpart + (size_t)(gwarp + b - um.b0) * TILE;
+            double* rp = P.rowpart + (size_t)(gwarp + l - um.l0) * TILE;
             rp[lane] = rs0;
             rp[lane + 32] = rs1;
             yv += rs0 * vi0 + rs1 * vi1;
             rs0 = rs1 = 0;
           }
-          if (endrow) { ++b; k = 0; newrow = true; }
+          if (endrow) {
+            ++l;
+            if (l < um.nl) b = __ldg(tab.ownI + l) - Bmin;
+            k = 0;
+            newrow = true;
+          }
         }
       }
       // dot-product units of this rank: global unit r = t * NR + rank
@@ -385,7 +403,7 @@ static __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel_mg(MgParams Q
       for (int base = j + 1; base < n; base += nslots) {  // trip count uniform within the warp (shuffles inside)
         const int i = base + slot;
         const bool live = i < n;
-        double acc = mg_row_partial(P, um, i, live, sub);
+        double acc = mg_row_partial(P, tab, um, i, live, sub);
 #pragma unroll
         for (int o = 1; o < TPR; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (live && sub < NR) ll_store(mg_vec(Q.xch[sub], par, rank, NR, xlen) + i, acc, flag);  // lane `sub` serves rank `sub`
@@ -478,12 +496,48 @@ static __global__ void __launch_bounds__(THREADS, 1) k_latrd_panel_mg(MgParams Q
 // xch[q]: exchange region of rank q as mapped here, mg_region_doubles(n, nranks) doubles.  epoch: 1 .. 65535, the same
 // on every rank and different from the epoch of the previous factorisation that used the regions (packet flags);
 // the regions are zeroed (and a barrier passed) whenever the epoch counter wraps.  n <= 65,535.  grid <= SM count CTAs.
+// host side of MgTab: `buf` holds mg_tab_bytes(n) bytes of device memory (8-byte aligned)
+inline size_t mg_tab_bytes(int64_t n) {
+  const size_t mB = (size_t)((n + TILE - 1) / TILE);
+  return (mB + 2) * sizeof(long long) + (2 * mB + 4) * sizeof(int);
+}
+inline cudaError_t mg_build_tab(int64_t n, int nranks, int rank, void* buf, cudaStream_t stream, MgTab* tab) {
+  const int mB = (int)((n + TILE - 1) / TILE);
+  std::vector<int> ownI, lfirst(mB + 1);
+  for (int I = 0; I < mB; ++I)
+    if (mg_owner_of_block_row(I, nranks) == rank) ownI.push_back(I);
+  const int nl = (int)ownI.size();
+  std::vector<long long> pref(nl + 1, 0);
+  for (int l = 0; l < nl; ++l) pref[l + 1] = pref[l] + (long long)SPT * (ownI[l] + 1);
+  for (int I = 0, l = 0; I <= mB; ++I) {
+    while (l < nl && ownI[l] < I) ++l;
+    lfirst[I] = l;
+  }
+  char* p = static_cast<char*>(buf);
+  long long* d_pref = reinterpret_cast<long long*>(p);
+  int* d_own = reinterpret_cast<int*>(p + (size_t)(mB + 2) * sizeof(long long));
+  int* d_lfirst = d_own + mB + 1;
+  cudaError_t st = cudaMemcpyAsync(d_pref, pref.data(), sizeof(long long) * (nl + 1), cudaMemcpyHostToDevice, stream);
+  if (st == cudaSuccess && nl > 0) st = cudaMemcpyAsync(d_own, ownI.data(), sizeof(int) * nl, cudaMemcpyHostToDevice, stream);
+  if (st == cudaSuccess) st = cudaMemcpyAsync(d_lfirst, lfirst.data(), sizeof(int) * (mB + 1), cudaMemcpyHostToDevice, stream);
+  if (st == cudaSuccess) st = cudaStreamSynchronize(stream);  // the host vectors die with this frame
+  tab->ownI = d_own; tab->pref = d_pref; tab->lfirst = d_lfirst; tab->nl = nl;
+  return st;
+}
+
+// `tabbuf`: mg_tab_bytes(n) bytes of device scratch for the ownership tables.  hooks->syr2k (when set) receives
+// the absolute first row of the trailing block and must leave this rank's 128-row groups of it and the whole of the
+// next panel's 64 columns current (eig.cu: sharded tcgen05 update + panel gather); the cuBLAS fall-back updates everything.
 inline cudaError_t run_mg(cublasHandle_t blas, cudaStream_t stream, double* A, int64_t n, int64_t lda, double* d, double* e,
-                          double* tau, double* work, int nranks, int rank, double* const* xch, unsigned epoch, int grid,
-                          int64_t* launches, const Hooks* hooks = nullptr) {
+                          double* tau, double* work, void* tabbuf, int nranks, int rank, double* const* xch, unsigned epoch,
+                          int grid, int64_t* launches, const Hooks* hooks = nullptr) {
   if (n < 1) return cudaSuccess;
   const int64_t mB = (n + TILE - 1) / TILE;
   MgParams Q;
+  {
+    cudaError_t st = mg_build_tab(n, nranks, rank, tabbuf, stream, &Q.tab);
+    if (st != cudaSuccess) return st;
+  }
   Params& P = Q.b;
   P.A = A; P.lda = lda; P.n = (int)n; P.d = d; P.e = e; P.tau = tau; P.mB = (int)mB;
   double* w = work;
@@ -519,7 +573,7 @@ inline cudaError_t run_mg(cublasHandle_t blas, cudaStream_t stream, double* A, i
     if (launches) ++*launches;
     const int64_t r0 = j0 + pw, nr = n - r0;
     if (nr > 0) {
-      st = trailing_update(blas, hooks, A + r0 + j0 * lda, lda, P.W + r0, n, nr, pw, A + r0 + r0 * lda, lda);
+      st = trailing_update(blas, hooks, A + r0 + j0 * lda, lda, P.W + r0, n, nr, pw, A + r0 + r0 * lda, lda, r0);
       if (st != cudaSuccess) return st;
     }
   }

@@ -721,7 +721,7 @@ def test_similarity_with_caller_neighbour_table():
 @pytest.mark.gpu
 def test_progress_callback_reports_err_and_interrupts():
     """rsoptsc_set_progress: one call per ADMM iteration carrying Err[iter, 1] (the value R prints at
-    R/SimilarityM.R:191), NMF stop checks every 10 iterations, and a non-zero return stops the run (status 7)."""
+    R/SimilarityM.R:191), NMF stop checks every 10 iterations, and a non-zero return stops the run (status 9)."""
     from rsoptsc_b200 import _lib
     p = small_problem(100, 220, seed=23)
     seen = []
@@ -738,7 +738,7 @@ def test_progress_callback_reports_err_and_interrupts():
         nmf = [s for s in seen if s[0] == 1]
         assert [s[1] for s in nmf] == list(range(10, c["iters"] + 1, 10))
         api.set_progress(lambda stage, it, v: stage == 0 and it == 3)
-        with pytest.raises(_lib.RsoptscError, match="error 7"):
+        with pytest.raises(_lib.RsoptscError, match="error 9"):
             api.computeM(None, p["X"], 0.5, idx=p["idx"])
     finally:
         api.set_progress(None)

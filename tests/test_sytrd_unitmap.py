@@ -65,3 +65,70 @@ def test_row_sum_slots_are_unique_and_complete(mt, ndot, warps):
             assert written.get(g + b) == {(g, b)}
         others = [slot for slot, v in written.items() if next(iter(v))[1] == b and not (g0 <= next(iter(v))[0] <= g1)]
         assert not others
+
+
+# ---- multi-GPU map (sytrd_mg.cuh): block row I (64 rows, absolute) belongs to rank (I // 2) % P for the whole
+# factorisation; per column the rank's units are the strips of its block rows at or below Bmin --------------------
+def mg_tables(mB, P, rank):
+    own = [I for I in range(mB) if (I >> 1) % P == rank]
+    pref = [0]
+    for I in own:
+        pref.append(pref[-1] + SPT * (I + 1))
+    lfirst, l = [], 0
+    for I in range(mB + 1):
+        while l < len(own) and own[l] < I:
+            l += 1
+        lfirst.append(l)
+    return own, pref, lfirst
+
+
+def mg_F(pref, l0, Bmin, l):
+    return pref[l] - pref[l0] - SPT * Bmin * (l - l0)
+
+
+def mg_local_row(own, pref, l0, nl, Bmin, P, u):
+    import math
+    bf = own[l0] - Bmin
+    b1 = bf + 1.0
+    l = l0 + int((math.sqrt(b1 * b1 + 2.0 * P * u / SPT) - b1) / P)
+    l = max(l0, min(l, nl - 1))
+    steps = 0
+    while l > l0 and mg_F(pref, l0, Bmin, l) > u:
+        l -= 1
+        steps += 1
+    while l + 1 < nl and mg_F(pref, l0, Bmin, l + 1) <= u:
+        l += 1
+        steps += 1
+    return l, steps
+
+
+@pytest.mark.parametrize("mB,P", list(itertools.product([1, 2, 3, 8, 33, 125], [2, 3, 4, 8])))
+def test_mg_cyclic_map_tiles_every_column_once(mB, P):
+    tabs = [mg_tables(mB, P, r) for r in range(P)]
+    assert sorted(I for own, _, _ in tabs for I in own) == list(range(mB))          # every block row has one owner
+    for Bmin in range(mB):
+        covered = set()
+        for r in range(P):
+            own, pref, lfirst = tabs[r]
+            nl, l0 = len(own), lfirst[Bmin]
+            strips = mg_F(pref, l0, Bmin, nl)
+            assert strips == sum(SPT * (I - Bmin + 1) for I in own if I >= Bmin)
+            worst = 0
+            for u in range(strips):
+                l, steps = mg_local_row(own, pref, l0, nl, Bmin, P, u)
+                worst = max(worst, steps)
+                k = u - mg_F(pref, l0, Bmin, l)
+                b = own[l] - Bmin
+                assert 0 <= k < SPT * (b + 1)
+                key = (own[l], k)
+                assert key not in covered
+                covered.add(key)
+            assert worst <= 3                                                         # the quadratic guess lands next to the answer
+        assert len(covered) == SPT * (mB - Bmin) * (mB - Bmin + 1) // 2                 # the whole trailing triangle
+    # balance: no rank streams more than one 128-row group above the mean
+    for Bmin in range(0, mB, 7):
+        per = []
+        for r in range(P):
+            own, pref, lfirst = tabs[r]
+            per.append(mg_F(pref, lfirst[Bmin], Bmin, len(own)))
+        assert max(per) - min(per) <= 2 * SPT * (mB - Bmin + 1)
