@@ -590,21 +590,51 @@ namespace oz {
 // Slicing of the paired operand [V | W] (nr rows, 2 x 64 contraction entries; V, W: nr x k with k <= 64, the unused
 // entries zero) straight from the two panels -- no packed copy.
 constexpr int PAIR_HALF = 64, PAIR_K = 2 * PAIR_HALF;
+// The two halves share one power-of-two exponent per row, so a row whose W entries dwarf its V entries (|v| <= 1,
+// |w| ~ ||A||) would slice V with fewer significant bits.  The operand is therefore [2^es V | 2^-es W] with ONE global
+// es = (exponent of max|W| - exponent of max|V|) / 2: the products V W^T and W V^T are unchanged (exact scaling),
+// both halves have comparable magnitude.  mx[0], mx[1]: bit patterns of max|V|, max|W| (k_pair_absmax).
+__global__ void k_pair_absmax(const double* __restrict__ V, long long ldv, const double* __restrict__ W, long long ldw, int nr, int k,
+                              unsigned long long* __restrict__ mx) {
+  double mv = 0, mw = 0;
+  for (int c = blockIdx.y; c < k; c += gridDim.y)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += gridDim.x * blockDim.x) {
+      mv = fmax(mv, abs_or_inf(V[i + (long long)c * ldv]));
+      mw = fmax(mw, abs_or_inf(W[i + (long long)c * ldw]));
+    }
+  for (int o = 16; o > 0; o >>= 1) {
+    mv = fmax(mv, __shfl_xor_sync(0xffffffffu, mv, o));
+    mw = fmax(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+  }
+  if ((threadIdx.x & 31) == 0) {  // non-negative doubles order like their bit patterns
+    atomicMax(mx, (unsigned long long)__double_as_longlong(mv));
+    atomicMax(mx + 1, (unsigned long long)__double_as_longlong(mw));
+  }
+}
+__device__ __forceinline__ int pair_es(const unsigned long long* __restrict__ mx) {
+  const double mv = __longlong_as_double((long long)mx[0]), mw = __longlong_as_double((long long)mx[1]);
+  if (!(mv > 0) || !(mw > 0) || !isfinite(mv) || !isfinite(mw)) return 0;
+  int ev, ew;
+  frexp(mv, &ev);
+  frexp(mw, &ew);
+  return max(-500, min(500, (ew - ev) / 2));
+}
 // operand row r = matrix row r - lead: the first `lead` operand rows are zero (they align the operand with absolute
 // 128-row groups; their outputs get +0)
 __device__ __forceinline__ double pair_value(const double* __restrict__ V, long long ldv, const double* __restrict__ W, long long ldw,
-                                             int r, int kk, int k, int lead) {
+                                             int r, int kk, int k, int lead, int es) {
   const int c = kk & (PAIR_HALF - 1);
   if (c >= k || r < lead) return 0.0;
-  return kk < PAIR_HALF ? V[(r - lead) + (long long)c * ldv] : W[(r - lead) + (long long)c * ldw];
+  return kk < PAIR_HALF ? V[(r - lead) + (long long)c * ldv] * pow2(es) : W[(r - lead) + (long long)c * ldw] * pow2(-es);
 }
 __global__ void k_rowmax_pair(const double* __restrict__ V, long long ldv, const double* __restrict__ W, long long ldw, int nr, int k,
-                              int lead, int* __restrict__ ex) {
+                              int lead, const unsigned long long* __restrict__ amax, int* __restrict__ ex) {
   __shared__ double sm[8][32];
   const int r = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;  // 32 rows x 8 column groups
+  const int es = pair_es(amax);
   double mx = 0;
   if (r < nr)
-    for (int kk = g; kk < PAIR_K; kk += 8) mx = fmax(mx, abs_or_inf(pair_value(V, ldv, W, ldw, r, kk, k, lead)));
+    for (int kk = g; kk < PAIR_K; kk += 8) mx = fmax(mx, abs_or_inf(pair_value(V, ldv, W, ldw, r, kk, k, lead, es)));
   sm[g][threadIdx.x & 31] = mx;
   __syncthreads();
   if (g == 0 && r < nr) {
@@ -615,15 +645,17 @@ __global__ void k_rowmax_pair(const double* __restrict__ V, long long ldv, const
   }
 }
 __global__ void k_slice_pair(const double* __restrict__ V, long long ldv, const double* __restrict__ W, long long ldw, int nr, int k,
-                             int lead, const int* __restrict__ ex, int S, int64_t Rp, int8_t* __restrict__ Q) {
+                             int lead, const unsigned long long* __restrict__ amax, const int* __restrict__ ex, int S, int64_t Rp,
+                             int8_t* __restrict__ Q) {
   __shared__ int8_t tile[MAXS][32][33];
   const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const int es = pair_es(amax);
   for (int kl = threadIdx.y; kl < 32; kl += blockDim.y) {
     const int r = r0 + threadIdx.x, kk = k0 + kl;
     int8_t q[MAXS];
 #pragma unroll
     for (int t = 0; t < MAXS; ++t) q[t] = 0;
-    if (r < nr) slice_value(pair_value(V, ldv, W, ldw, r, kk, k, lead), ex[r], S, q);
+    if (r < nr) slice_value(pair_value(V, ldv, W, ldw, r, kk, k, lead, es), ex[r], S, q);
     for (int t = 0; t < S; ++t) tile[t][threadIdx.x][kl] = q[t];
   }
   __syncthreads();
@@ -666,13 +698,16 @@ void ozaki_syr2k_lower_sub(const double* V, int64_t ldv, const double* W, int64_
   a.Rp = (rows + oz::ROWPAD - 1) / oz::ROWPAD * oz::ROWPAD;
   a.Kp = oz::PAIR_K;
   a.Q.alloc((size_t)a.S * a.Rp * a.Kp);
-  a.ex.alloc(a.Rp);
+  a.ex.alloc(a.Rp + 4);  // + two 64-bit slots for max|V|, max|W| (a.Rp is a multiple of 128: 8-byte aligned)
+  unsigned long long* amax = reinterpret_cast<unsigned long long*>(a.ex.p + a.Rp);
   {
     Phase ph("ozaki_slice");
-    RS_CUDA(cudaMemsetAsync(a.ex.p, 0, sizeof(int) * a.Rp, ctx().stream));
-    RS_LAUNCH(oz::k_rowmax_pair, (unsigned)cdiv(rows, 32), 256, 0, V, (long long)ldv, W, (long long)ldw, (int)rows, k, lead, a.ex.p);
+    RS_CUDA(cudaMemsetAsync(a.ex.p, 0, sizeof(int) * (a.Rp + 4), ctx().stream));
+    dim3 gmax((unsigned)std::min<int64_t>(cdiv(nr, 256), 16), (unsigned)std::min(k, 16));
+    RS_LAUNCH(oz::k_pair_absmax, gmax, 256, 0, V, (long long)ldv, W, (long long)ldw, (int)nr, k, amax);
+    RS_LAUNCH(oz::k_rowmax_pair, (unsigned)cdiv(rows, 32), 256, 0, V, (long long)ldv, W, (long long)ldw, (int)rows, k, lead, amax, a.ex.p);
     dim3 grid(oz::PAIR_K / 32, (unsigned)(a.Rp / 32)), block(32, 8);
-    RS_LAUNCH(oz::k_slice_pair, grid, block, 0, V, (long long)ldv, W, (long long)ldw, (int)rows, k, lead, a.ex.p, a.S, a.Rp, a.Q.p);
+    RS_LAUNCH(oz::k_slice_pair, grid, block, 0, V, (long long)ldv, W, (long long)ldw, (int)rows, k, lead, amax, a.ex.p, a.S, a.Rp, a.Q.p);
   }
   std::vector<char> mine;
   if (nranks > 1) {
