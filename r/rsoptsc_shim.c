@@ -292,7 +292,36 @@ SEXP rsoptsc_R_signaling_pair(SEXP lig, SEXP rec, SEXP beta, SEXP gamma) {
   return P;
 }
 
+/* Multi-GPU: one R worker per GPU.  .Call("rsoptsc_R_init", device);
+ * id <- .Call("rsoptsc_R_comm_unique_id") on rank 0 (raw vector of 128 bytes, handed to the other workers by the host's
+ * own channel, e.g. parallel::clusterExport); .Call("rsoptsc_R_comm_init", nranks, rank, id) on every worker; from then
+ * on every worker makes the SAME SimilarityM / computeM call and the library splits the one problem. */
+SEXP rsoptsc_R_init(SEXP device) {
+  check(rsoptsc_init(Rf_asInteger(device)));
+  return R_NilValue;
+}
+SEXP rsoptsc_R_comm_unique_id(void) {
+  SEXP id = PROTECT(Rf_allocVector(RAWSXP, 128));
+  int st = rsoptsc_comm_unique_id((uint8_t*)RAW(id));
+  if (st != 0) { UNPROTECT(1); check(st); }
+  UNPROTECT(1);
+  return id;
+}
+SEXP rsoptsc_R_comm_init(SEXP nranks, SEXP rank, SEXP id) {
+  if (Rf_xlength(id) != 128) Rf_error("the NCCL unique id is a raw vector of 128 bytes");
+  check(rsoptsc_comm_init(Rf_asInteger(nranks), Rf_asInteger(rank), (const uint8_t*)RAW(id)));
+  return R_NilValue;
+}
+SEXP rsoptsc_R_comm_finalize(void) {
+  check(rsoptsc_comm_finalize());
+  return R_NilValue;
+}
+
 static const R_CallMethodDef call_methods[] = {
+    {"rsoptsc_R_init", (DL_FUNC)&rsoptsc_R_init, 1},
+    {"rsoptsc_R_comm_unique_id", (DL_FUNC)&rsoptsc_R_comm_unique_id, 0},
+    {"rsoptsc_R_comm_init", (DL_FUNC)&rsoptsc_R_comm_init, 3},
+    {"rsoptsc_R_comm_finalize", (DL_FUNC)&rsoptsc_R_comm_finalize, 0},
     {"rsoptsc_R_graph_distances", (DL_FUNC)&rsoptsc_R_graph_distances, 1},
     {"rsoptsc_R_dist_flat", (DL_FUNC)&rsoptsc_R_dist_flat, 1},
     {"rsoptsc_R_signaling_pair", (DL_FUNC)&rsoptsc_R_signaling_pair, 4},

@@ -11,9 +11,11 @@ typedef enum { FALSE = 0, TRUE } Rboolean;
 #define REALSXP 14
 #define STRSXP 16
 #define VECSXP 19
+#define RAWSXP 24
 extern SEXP R_NilValue, R_DimSymbol, R_NamesSymbol;
 double* REAL(SEXP x);
 int* INTEGER(SEXP x);
+unsigned char* RAW(SEXP x);
 SEXP Rf_getAttrib(SEXP x, SEXP name);
 SEXP Rf_setAttrib(SEXP x, SEXP name, SEXP val);
 SEXP Rf_allocVector(unsigned int type, R_xlen_t n);
