@@ -167,6 +167,15 @@ int rsoptsc_nmf_lee(const double* V, int64_t n, int32_t k, int32_t max_iter, dou
 int rsoptsc_nmf_lee_dev(const double* d_V, int64_t n, int32_t k, int32_t max_iter,
                         double* basis, double* coef, int32_t* labels, int32_t* iters);
 
+/* Rank sweep: nmf(V, k, 'lee', 'nndsvd') + labels for every k in k_lo .. k_hi on ONE similarity matrix (BASELINE.json
+ * configs[3]: k = 5..30; the reference would call ClusterCells once per k, R/Clustering.R:29-37).  The independent
+ * problems advance together, one batched launch set per iteration; every k gets exactly the labels and iteration
+ * count of a separate rsoptsc_nmf_lee call.  labels: (k_hi - k_lo + 1) x n row-major, 1-based; iters: one per k. */
+int rsoptsc_nmf_sweep(const double* V, int64_t n, int32_t k_lo, int32_t k_hi, int32_t max_iter,
+                      int32_t* labels, int32_t* iters);
+int rsoptsc_nmf_sweep_dev(const double* d_V, int64_t n, int32_t k_lo, int32_t k_hi, int32_t max_iter,
+                          int32_t* labels, int32_t* iters);
+
 /* ---- CountClusters stages --------------------------------------------------------- */
 /* a14  GetComponents(data, tol)  R/Clustering.R:96-105: ascending |eigenvalues| of the
  * symmetric normalised Laplacian of S (n x n) and the count <= tol. */

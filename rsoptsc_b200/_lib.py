@@ -61,6 +61,8 @@ SIGNATURES = {
                                   c_int32_p]),
     "rsoptsc_nmf_lee_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, c_double_p, c_double_p, c_int32_p,
                                       c_int32_p]),
+    "rsoptsc_nmf_sweep": (C.c_int, [c_double_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_int32_p, c_int32_p]),
+    "rsoptsc_nmf_sweep_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_int32_p, c_int32_p]),
     "rsoptsc_get_components": (C.c_int, [c_double_p, C.c_int64, C.c_double, c_double_p, c_int32_p]),
     "rsoptsc_consensus": (C.c_int, [c_int32_p, C.c_int32, C.c_int64, C.c_double, c_double_p]),
     "rsoptsc_get_ensemble": (C.c_int, [c_double_p, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_int32, c_double_p]),

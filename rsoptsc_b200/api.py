@@ -181,6 +181,20 @@ def nmf_lee(V, rank, max_iter=2000):
     return dict(W=basis, H=coef, labels=labels, iters=int(iters.value))
 
 
+def nmf_sweep(V, ranks=(5, 30), max_iter=2000):
+    """nmf(V, k, 'lee', 'nndsvd') labels for every k in ranks[0] .. ranks[1] (BASELINE.json configs[3]), the
+    independent problems batched on the GPU -> dict(ranks, labels (R x n, 1-based), iters (R))."""
+    lib = _lib.init()
+    v = _f64(V)
+    n = v.shape[0]
+    k_lo, k_hi = int(min(ranks)), int(max(ranks))
+    R = k_hi - k_lo + 1
+    labels = np.empty((R, n), dtype=np.int32)
+    iters = np.empty(R, dtype=np.int32)
+    _lib.check(lib.rsoptsc_nmf_sweep(_dp(v), n, k_lo, k_hi, int(max_iter), _ip(labels), _ip(iters)))
+    return dict(ranks=list(range(k_lo, k_hi + 1)), labels=labels, iters=iters)
+
+
 def GetComponents(data, tol=0.01):
     """R/Clustering.R:96-105 -> dict(val ascending, n_eigs)."""
     lib = _lib.init()

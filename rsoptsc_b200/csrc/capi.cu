@@ -567,6 +567,24 @@ int rsoptsc_nmf_lee(const double* V, int64_t n, int32_t k, int32_t max_iter, dou
   });
 }
 
+int rsoptsc_nmf_sweep(const double* V, int64_t n, int32_t k_lo, int32_t k_hi, int32_t max_iter, int32_t* labels,
+                      int32_t* iters) {
+  return guarded([&] {
+    cudaStream_t s = ctx().stream;
+    RS_REQUIRE(V && n > 0, "nmf_sweep: empty matrix");
+    DevBuf<double> d((size_t)n * n);
+    d.upload(V, (size_t)n * n, s);
+    nmf_sweep(d.p, n, k_lo, k_hi, max_iter, labels, iters);
+  });
+}
+int rsoptsc_nmf_sweep_dev(const double* d_V, int64_t n, int32_t k_lo, int32_t k_hi, int32_t max_iter, int32_t* labels,
+                          int32_t* iters) {
+  return guarded([&] {
+    ctx();
+    nmf_sweep(d_V, n, k_lo, k_hi, max_iter, labels, iters);
+  });
+}
+
 // ---- a14-a18 ----------------------------------------------------------------------------
 int rsoptsc_get_components(const double* S, int64_t n, double tol, double* vals, int32_t* n_eigs) {
   return guarded([&] {

@@ -176,6 +176,10 @@ struct NmfResult { int iters = 0; };
 void nmf_lee(const double* d_V, int64_t n, int k, int max_iter, double* h_basis, double* h_coef,
              int32_t* h_labels, NmfResult& res);
 
+// rank sweep k = k_lo .. k_hi on one similarity matrix, all problems advanced together (batched launches);
+// h_labels: (k_hi - k_lo + 1) x n row-major, 1-based; h_iters: iterations of every rank
+void nmf_sweep(const double* d_V, int64_t n, int k_lo, int k_hi, int max_iter, int32_t* h_labels, int32_t* h_iters);
+
 // graph.cu (RepresentationMap pieces)
 void dist_flat(const double* d_emb, int64_t n, int dim, double* d_D);
 void adjacency(const double* d_S, int64_t n, double* d_A);

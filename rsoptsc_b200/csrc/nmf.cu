@@ -108,8 +108,8 @@ void spmv(const Compressed& A, const double* x, double* y) {
 }
 
 // ---- k x k Gram of a cell-major n x k factor, column sums -----------------------------------
-__global__ void k_gram_partial(const double* __restrict__ O, int64_t n, int k, double* __restrict__ partial) {
-  extern __shared__ double tile[];  // 32 rows x k
+__device__ __forceinline__ void d_gram_partial(const double* __restrict__ O, int64_t n, int k, double* __restrict__ partial,
+                                               double* tile /* shared: 32 rows x k */) {
   const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
   const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(n, r0 + chunk);
   const int kk = k * k;
@@ -132,14 +132,21 @@ __global__ void k_gram_partial(const double* __restrict__ O, int64_t n, int k, d
   int u = 0;
   for (int e = threadIdx.x; e < kk; e += NT, ++u) partial[(int64_t)blockIdx.x * kk + e] = acc[u];
 }
-__global__ void k_gram_final(const double* __restrict__ partial, int P, int kk, double* __restrict__ G) {
+__global__ void k_gram_partial(const double* __restrict__ O, int64_t n, int k, double* __restrict__ partial) {
+  extern __shared__ double tile[];  // 32 rows x k
+  d_gram_partial(O, n, k, partial, tile);
+}
+__device__ __forceinline__ void d_gram_final(const double* __restrict__ partial, int P, int kk, double* __restrict__ G) {
   const int e = blockIdx.x * NT + threadIdx.x;
   if (e >= kk) return;
   double s = 0;
   for (int p = 0; p < P; ++p) s += partial[(int64_t)p * kk + e];
   G[e] = s;
 }
-__global__ void k_colsum_partial(const double* __restrict__ O, int64_t n, int k, double* __restrict__ partial) {
+__global__ void k_gram_final(const double* __restrict__ partial, int P, int kk, double* __restrict__ G) {
+  d_gram_final(partial, P, kk, G);
+}
+__device__ __forceinline__ void d_colsum_partial(const double* __restrict__ O, int64_t n, int k, double* __restrict__ partial) {
   // thread c < k sums column c over this block's rows (k <= NT)
   const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
   const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(n, r0 + chunk);
@@ -149,8 +156,11 @@ __global__ void k_colsum_partial(const double* __restrict__ O, int64_t n, int k,
     partial[(int64_t)blockIdx.x * k + threadIdx.x] = s;
   }
 }
-__global__ void k_rescale(double* __restrict__ W, int64_t n, int k, const double* __restrict__ partial, int P) {
-  __shared__ double cs[NMF_KMAX];
+__global__ void k_colsum_partial(const double* __restrict__ O, int64_t n, int k, double* __restrict__ partial) {
+  d_colsum_partial(O, n, k, partial);
+}
+__device__ __forceinline__ void d_rescale(double* __restrict__ W, int64_t n, int k, const double* __restrict__ partial, int P,
+                                          double* cs /* shared: NMF_KMAX */) {
   if (threadIdx.x < k) {
     double s = 0;
     for (int p = 0; p < P; ++p) s += partial[(int64_t)p * k + threadIdx.x];
@@ -160,13 +170,16 @@ __global__ void k_rescale(double* __restrict__ W, int64_t n, int k, const double
   const int64_t total = n * k;
   for (int64_t e = (int64_t)blockIdx.x * NT + threadIdx.x; e < total; e += (int64_t)gridDim.x * NT) W[e] /= cs[e % k];
 }
+__global__ void k_rescale(double* __restrict__ W, int64_t n, int k, const double* __restrict__ partial, int P) {
+  __shared__ double cs[NMF_KMAX];
+  d_rescale(W, n, k, partial, P, cs);
+}
 
 // ---- multiplicative update of one factor (warp per cell) -------------------------------------
 // T[x][c] <- max(T[x][c] * sum_e val[e] O[idx[e]][c], eps) / (sum_c' G[c][c'] T[x][c'] + eps)
-__global__ void k_mult_update(const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
-                              int64_t n, int k, const double* __restrict__ O, const double* __restrict__ G, double eps,
-                              double* __restrict__ T) {
-  extern __shared__ double sm[];   // G (k*k) + per-warp old row (k each)
+__device__ __forceinline__ void d_mult_update(const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
+                                              int64_t n, int k, const double* __restrict__ O, const double* __restrict__ G, double eps,
+                                              double* __restrict__ T, double* sm /* shared: G (k*k) + per-warp old row (k each) */) {
   double* sG = sm;
   double* sT = sm + k * k + (threadIdx.x >> 5) * k;
   for (int e = threadIdx.x; e < k * k; e += NT) sG[e] = G[e];
@@ -185,10 +198,16 @@ __global__ void k_mult_update(const int* __restrict__ ptr, const int* __restrict
     T[x * k + c] = fmax(sT[c] * num, eps) / (den + eps);
   }
 }
+__global__ void k_mult_update(const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
+                              int64_t n, int k, const double* __restrict__ O, const double* __restrict__ G, double eps,
+                              double* __restrict__ T) {
+  extern __shared__ double sm[];
+  d_mult_update(ptr, idx, val, n, k, O, G, eps, T, sm);
+}
 
 // first arg-max of every cell's k-vector; optional comparison with a previous assignment
-__global__ void k_argmax(const double* __restrict__ F, int64_t n, int k, int base, int32_t* __restrict__ out,
-                         const int32_t* __restrict__ prev, int* __restrict__ changed) {
+__device__ __forceinline__ void d_argmax(const double* __restrict__ F, int64_t n, int k, int base, int32_t* __restrict__ out,
+                                         const int32_t* __restrict__ prev, int* __restrict__ changed) {
   const int64_t x = (int64_t)blockIdx.x * NT + threadIdx.x;
   if (x >= n) return;
   int best = 0;
@@ -199,6 +218,55 @@ __global__ void k_argmax(const double* __restrict__ F, int64_t n, int k, int bas
   }
   out[x] = best + base;
   if (prev && prev[x] != best + base) *changed = 1;
+}
+__global__ void k_argmax(const double* __restrict__ F, int64_t n, int k, int base, int32_t* __restrict__ out,
+                         const int32_t* __restrict__ prev, int* __restrict__ changed) {
+  d_argmax(F, n, k, base, out, prev, changed);
+}
+
+// ---- batched forms: blockIdx.y = problem of a rank sweep (same arithmetic as the single-problem kernels) ----------
+struct NmfProb {
+  double *W, *H, *G, *part;
+  int32_t *cur, *prev;
+  int* changed;
+  int k, done, have_prev;
+};
+__global__ void kb_gram_partial(const NmfProb* __restrict__ pr, int of_H, int64_t n) {
+  extern __shared__ double tile[];
+  const NmfProb P = pr[blockIdx.y];
+  if (P.done) return;
+  d_gram_partial(of_H ? P.H : P.W, n, P.k, P.part, tile);
+}
+__global__ void kb_gram_final(const NmfProb* __restrict__ pr, int nparts) {
+  const NmfProb P = pr[blockIdx.y];
+  if (P.done) return;
+  d_gram_final(P.part, nparts, P.k * P.k, P.G);
+}
+// update_H != 0: H <- f(W, G = W^T W) over the CSC view; else W <- f(H, G = H H^T) over the CSR view
+__global__ void kb_mult_update(const NmfProb* __restrict__ pr, int update_H, const int* __restrict__ ptr, const int* __restrict__ idx,
+                               const double* __restrict__ val, int64_t n, double eps) {
+  extern __shared__ double sm[];
+  const NmfProb P = pr[blockIdx.y];
+  if (P.done) return;
+  d_mult_update(ptr, idx, val, n, P.k, update_H ? P.W : P.H, P.G, eps, update_H ? P.H : P.W, sm);
+}
+__global__ void kb_colsum_partial(const NmfProb* __restrict__ pr, int64_t n) {
+  const NmfProb P = pr[blockIdx.y];
+  if (P.done) return;
+  d_colsum_partial(P.W, n, P.k, P.part);
+}
+__global__ void kb_rescale(const NmfProb* __restrict__ pr, int64_t n, int nparts) {
+  __shared__ double cs[NMF_KMAX];
+  const NmfProb P = pr[blockIdx.y];
+  if (P.done) return;
+  d_rescale(P.W, n, P.k, P.part, nparts, cs);
+}
+// on_basis != 0: final labels from W (1-based) into cur; else the connectivity check on H against prev
+__global__ void kb_argmax(const NmfProb* __restrict__ pr, int64_t n, int on_basis) {
+  const NmfProb P = pr[blockIdx.y];
+  if (on_basis) { d_argmax(P.W, n, P.k, 1, P.cur, nullptr, P.changed); return; }
+  if (P.done) return;
+  d_argmax(P.H, n, P.k, 0, P.cur, P.have_prev ? P.prev : nullptr, P.changed);
 }
 
 // ---- NNDSVD seed ----------------------------------------------------------------------------
@@ -401,6 +469,121 @@ void nmf_lee(const double* d_V, int64_t n, int k, int max_iter, double* h_basis,
   if (h_basis)
     for (int64_t r = 0; r < n; ++r)
       for (int c = 0; c < k; ++c) h_basis[r + (int64_t)c * n] = hw[r * k + c];
+}
+
+// ---- rank sweep (BASELINE.json configs[3]: nmf(V, k) for k = k_lo .. k_hi) ---------------------------------------
+// The R problems are independent and each is launch-bound (8 small kernels per iteration): they advance together,
+// one batched launch set per iteration with blockIdx.y = problem, V compressed once.  Every problem runs exactly the
+// arithmetic of nmf_lee (same device functions, same seed routine), so labels and iteration counts are those of R
+// separate calls; a problem that meets its stop rule is frozen (its blocks exit) while the others go on.
+void nmf_sweep(const double* d_V, int64_t n, int k_lo, int k_hi, int max_iter, int32_t* h_labels, int32_t* h_iters) {
+  cudaStream_t s = ctx().stream;
+  RS_REQUIRE(n > 0, "nmf_sweep: empty matrix");
+  RS_REQUIRE(k_lo >= 1 && k_hi >= k_lo && k_hi <= NMF_KMAX && k_hi <= n, "nmf_sweep: ranks must satisfy 1 <= k_lo <= k_hi <= min(n, 128)");
+  if (max_iter <= 0) max_iter = 2000;
+  const double eps = 1e-9;
+  const int stop_conv = 40, check_interval = 10;
+  const int R = k_hi - k_lo + 1, kmax = k_hi;
+  Compressed csr, csc;
+  compress(d_V, n, true, csr);
+  compress(d_V, n, false, csc);
+  std::vector<DevBuf<double>> W(R), H(R), G(R), part(R);
+  std::vector<DevBuf<int32_t>> ia(R), ib(R);
+  DevBuf<int> changed(R);
+  std::vector<NmfProb> prob(R);
+  for (int p = 0; p < R; ++p) {
+    const int k = k_lo + p;
+    std::vector<double> W0, H0;
+    nndsvd_seed(d_V, csr, csc, n, k, W0, H0);
+    W[p].alloc((size_t)n * k); H[p].alloc((size_t)n * k); G[p].alloc((size_t)k * k);
+    part[p].alloc((size_t)GP * std::max(k * k, k));
+    ia[p].alloc(n); ib[p].alloc(n);
+    W[p].upload(W0.data(), W0.size(), s);
+    H[p].upload(H0.data(), H0.size(), s);
+    RS_CUDA(cudaStreamSynchronize(s));  // W0 / H0 die with this iteration
+    prob[p] = NmfProb{W[p].p, H[p].p, G[p].p, part[p].p, ia[p].p, ib[p].p, changed.p + p, k, 0, 0};
+  }
+  Phase ph("nmf");
+  DevBuf<NmfProb> d_prob(R);
+  auto push = [&] { d_prob.upload(prob.data(), R, s); RS_CUDA(cudaStreamSynchronize(s)); };
+  push();
+  const unsigned wgrid = (unsigned)cdiv(n * 32, NT);
+  const size_t upd_smem = sizeof(double) * ((size_t)kmax * kmax + (NT / 32) * kmax);
+  const size_t gram_smem = sizeof(double) * 32 * kmax;
+  if (upd_smem > 48 * 1024)
+    RS_CUDA(cudaFuncSetAttribute(kb_mult_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
+  const unsigned Ry = (unsigned)R;
+  auto one_iteration = [&] {
+    RS_LAUNCH(kb_gram_partial, dim3(GP, Ry), NT, gram_smem, d_prob.p, 0, n);
+    RS_LAUNCH(kb_gram_final, dim3((unsigned)cdiv(kmax * kmax, NT), Ry), NT, 0, d_prob.p, GP);
+    RS_LAUNCH(kb_mult_update, dim3(wgrid, Ry), NT, upd_smem, d_prob.p, 1, csc.ptr.p, csc.idx.p, csc.val.p, n, eps);
+    RS_LAUNCH(kb_gram_partial, dim3(GP, Ry), NT, gram_smem, d_prob.p, 1, n);
+    RS_LAUNCH(kb_gram_final, dim3((unsigned)cdiv(kmax * kmax, NT), Ry), NT, 0, d_prob.p, GP);
+    RS_LAUNCH(kb_mult_update, dim3(wgrid, Ry), NT, upd_smem, d_prob.p, 0, csr.ptr.p, csr.idx.p, csr.val.p, n, eps);
+    RS_LAUNCH(kb_colsum_partial, dim3(GP, Ry), NT, 0, d_prob.p, n);
+    RS_LAUNCH(kb_rescale, dim3(148 * 2, Ry), NT, 0, d_prob.p, n, GP);
+  };
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  const int64_t launches_before = g_launches.load();
+  RS_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  try {
+    for (int r = 0; r < check_interval; ++r) one_iteration();
+  } catch (...) {
+    cudaStreamEndCapture(s, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    throw;
+  }
+  RS_CUDA(cudaStreamEndCapture(s, &graph));
+  const int64_t launches_per_graph = g_launches.load() - launches_before;
+  g_launches.fetch_sub(launches_per_graph);
+  RS_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+  struct GraphGuard {
+    cudaGraph_t g; cudaGraphExec_t e;
+    ~GraphGuard() { if (e) cudaGraphExecDestroy(e); if (g) cudaGraphDestroy(g); }
+  } guard{graph, gexec};
+  std::vector<int> inc(R, 0), iters(R, 0), hc(R, 0);
+  int live = R, it = 0;
+  const int full = max_iter / check_interval * check_interval;  // iterations covered by whole graphs
+  while (live > 0 && it < max_iter) {
+    if (it < full) {
+      RS_CUDA(cudaGraphLaunch(gexec, s));
+      g_launches.fetch_add(launches_per_graph);
+      it += check_interval;
+    } else {
+      one_iteration();
+      ++it;
+    }
+    if (it % check_interval == 0) {  // 'connectivity' stop of every live problem
+      changed.zero(s);
+      RS_LAUNCH(kb_argmax, dim3((unsigned)cdiv(n, NT), Ry), NT, 0, d_prob.p, n, 0);
+      RS_CUDA(cudaMemcpyAsync(hc.data(), changed.p, sizeof(int) * R, cudaMemcpyDeviceToHost, s));
+      RS_CUDA(cudaStreamSynchronize(s));
+      for (int p = 0; p < R; ++p) {
+        if (prob[p].done) continue;
+        if (prob[p].have_prev && !hc[p]) {
+          ++inc[p];
+        } else {
+          std::swap(prob[p].cur, prob[p].prev);
+          prob[p].have_prev = 1;
+          inc[p] = 0;
+        }
+        if (inc[p] > stop_conv) { prob[p].done = 1; iters[p] = it; --live; }
+      }
+      push();
+      report_progress(/*RSOPTSC_STAGE_NMF*/ 1, it, 0.0);
+    }
+  }
+  for (int p = 0; p < R; ++p)
+    if (!prob[p].done) iters[p] = std::min(it, max_iter);
+  if (h_labels) {
+    RS_LAUNCH(kb_argmax, dim3((unsigned)cdiv(n, NT), Ry), NT, 0, d_prob.p, n, 1);
+    for (int p = 0; p < R; ++p)
+      RS_CUDA(cudaMemcpyAsync(h_labels + (size_t)p * n, prob[p].cur, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+  }
+  RS_CUDA(cudaStreamSynchronize(s));
+  if (h_iters)
+    for (int p = 0; p < R; ++p) h_iters[p] = iters[p];
 }
 
 }  // namespace rs

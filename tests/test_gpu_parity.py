@@ -784,3 +784,22 @@ def test_gemm_propagates_nonfinite_operands(backend):
     ref = np.delete(np.delete(A, 5, axis=0) @ np.delete(B, 3, axis=1), [], axis=0)
     got = np.delete(np.delete(Cc, 5, axis=0), 3, axis=1)
     assert relF(got, ref) < 1e-12
+
+
+@pytest.mark.gpu
+def test_nmf_rank_sweep_equals_separate_calls(joost):
+    """configs[3]: the batched rank sweep gives, for every k, exactly the labels and the iteration count of a separate
+    nmf call (fixture similarity, k = 5..12; k = 9 is the reference's own stored answer: 510 iterations)."""
+    S = joost["S"]
+    sw = api.nmf_sweep(S, ranks=(5, 12))
+    assert sw["ranks"] == list(range(5, 13))
+    for p, k in enumerate(sw["ranks"]):
+        one = api.nmf_lee(S, k)
+        assert sw["iters"][p] == one["iters"], (k, sw["iters"][p], one["iters"])
+        assert np.array_equal(sw["labels"][p], one["labels"]), k
+    assert sw["iters"][sw["ranks"].index(9)] == 510
+    assert np.array_equal(sw["labels"][sw["ranks"].index(9)], np.asarray(joost["labels"]))
+    # a capped sweep stops every problem at the cap
+    capped = api.nmf_sweep(S, ranks=(5, 6), max_iter=25)
+    assert list(capped["iters"]) == [25, 25]
+    assert np.array_equal(capped["labels"][0], api.nmf_lee(S, 5, max_iter=25)["labels"])
