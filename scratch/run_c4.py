@@ -26,12 +26,14 @@ print("CountClusters: %.1f s upper=%d lower=%d  phases=%s" % (t_cc, cc["upper_bo
       {k: round(v["ms"]) for k, v in api.phase_report().items()}), flush=True)
 api.timers(False)
 t = time.time()
-res = {}
-for k in range(5, 31):
-    res[k] = api.nmf_lee(W, k)
+sw = api.nmf_sweep(W, ranks=(5, 30))
 t_sweep = time.time() - t
-print("NMF rank sweep k=5..30: %.1f s, iters=%s" % (t_sweep, [res[k]["iters"] for k in sorted(res)]), flush=True)
-lab = res[10]["labels"]
+print("NMF rank sweep k=5..30 (batched, rsoptsc_nmf_sweep): %.1f s, iters=%s" % (t_sweep, list(sw["iters"])), flush=True)
+t = time.time()
+one = api.nmf_lee(W, 10)
+print("single nmf_lee k=10: %.2f s, iters=%d, labels equal to the sweep's: %s"
+      % (time.time() - t, one["iters"], bool(np.array_equal(one["labels"], sw["labels"][5]))), flush=True)
+lab = sw["labels"][5]
 from scipy.special import comb  # noqa: E402
 cont = np.zeros((10, planted.max() + 1))
 np.add.at(cont, (lab - 1, planted), 1)
