@@ -246,6 +246,9 @@ void run_admm(const double* d_X, int64_t m, int64_t n, const Support& s, double 
     std::vector<double> a_f2;
     build_A(s, st.Zs.p, Y3.p, mu, A.p, a_f2, pp);
     bool any_J = false;
+    std::vector<double*> small_blocks;   // small blocks with J != 0: batched below (svt_small_batch)
+    std::vector<int64_t> small_sizes;
+    const int64_t small_lim = svt_small_limit();
     for (size_t cidx = 0; cidx < s.comp_n.size(); ++cidx) {
       if (!mine(cidx)) continue;
       const int64_t nc = s.comp_n[cidx];
@@ -259,11 +262,14 @@ void run_admm(const double* d_X, int64_t m, int64_t n, const Support& s, double 
         RS_CUDA(cudaMemsetAsync(Ac, 0, sizeof(double) * nc * nc, c.stream));
       } else {
         if (sh && plan.big[cidx]) svt_sharded(svt, Ac, nc, tau, plan.cb[cidx]);
+        else if (nc >= 2 && nc < small_lim) { small_blocks.push_back(Ac); small_sizes.push_back(nc); }
         else svt_inplace(svt, Ac, nc, tau);
         ++res.n_svt;
         any_J = true;
       }
     }
+    if (small_blocks.size() >= 2) svt_small_batch(small_blocks, small_sizes, tau);
+    else if (small_blocks.size() == 1) svt_inplace(svt, small_blocks[0], small_sizes[0], tau);
     const double* J = any_J ? A.p : nullptr;
     gather_support_term(s, st.Zs.p, J, Y3.p, mu, st.q.p, pp);  // (Z - J + Y3/mu) on the support
     admm_E_update(st, lambda, mu);                           // R :164-176

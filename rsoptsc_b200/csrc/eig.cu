@@ -142,6 +142,16 @@ static int64_t native_min_n() {
   return t;
 }
 
+// Blocks below this size go through cusolverDnXsyevd and cuBLAS Grams anyway: run_admm may batch them (svt.cu)
+int64_t svt_small_limit() {
+  const char* off = getenv("RSOPTSC_SVT_BATCH");
+  if (off && off[0] == '0') return 0;
+  // the batch route forms its Grams with cuBLAS: stay below the size where the tcgen05 kernel takes them over
+  const int64_t gemm_lim = gemm_backend() == 2 ? 256 : 1536;
+  const int64_t lim = std::min<int64_t>(native_min_n() < 0 ? gemm_lim : native_min_n(), gemm_lim);
+  return std::max<int64_t>(lim, 0);
+}
+
 // trailing update of the tridiagonalisation on the library's own GEMM (tcgen05 split-integer kernel, gemm.cu)
 // user: null = update the whole block; else int[2] {nranks, rank}: this rank's 128-row groups only (sytrd_mg.cu)
 void sytrd_trailing_update(const double* V, long long ldv, const double* W, long long ldw, long long nr, int k, double* C,

@@ -142,6 +142,11 @@ struct SvtWorkspace {
 };
 // J = SVT_tau(A) written over A.  Returns rank(J).
 int64_t svt_inplace(SvtWorkspace& ws, double* d_A, int64_t n, double tau);
+// Several small blocks (every size below svt_small_limit()) with the same tau: Gram + eigensolve of the blocks side by
+// side on two extra streams, reconstructions on the library stream.  J over every block.
+void svt_small_batch(const std::vector<double*>& blocks, const std::vector<int64_t>& sizes, double tau);
+// largest block size the batch route takes (0: route off -- native eigensolver forced, RSOPTSC_SVT_BATCH=0, ...)
+int64_t svt_small_limit();
 // Collective variant for a block replicated on every rank (comm.h): on return the columns
 // [cb[rank], cb[rank+1]) of d_A hold J, the other columns are unspecified.
 int64_t svt_sharded(SvtWorkspace& ws, double* d_A, int64_t n, double tau, const std::vector<int64_t>& cb);
