@@ -360,9 +360,10 @@ def main():
             return {"kernel": "k_ozaki_gemm<8> (tcgen05.mma kind::i8, FP64-equivalent)", "bound": "tensor",
                     "achieved": oz_flops / osec / 1e12, "peak": 2.0 * bf16 / pairs, "unit": "TFLOP/s",
                     "frac": (oz_flops / osec / 1e12) / (2.0 * bf16 / pairs),
-                    "traffic": 13.43e9,
+                    "traffic": 15.35e9,
                     "traffic_note": "dram read+write of ONE launch, the n=10000 Gram, from ncu --set full "
-                                    "(profiles/r1_ozaki_gemm_ncu_full.csv): tensor-bound, DRAM at 11 %",
+                                    "(profiles/r2_ozaki_gemm_ncu_full.csv): 14.5 GB read + 0.8 GB written, DRAM at 14 %, "
+                                    "tensor pipe active 72 %, bound by L2 -> SM operand traffic",
                     "int8_tops_achieved": oz_iops / osec / 1e12, "int8_tops_peak": 2.0 * bf16,
                     "peak_source": "2 x %s (int8 runs at twice the bf16 rate) / %d int8 slice-pair MMAs per FP64 MAC"
                                    % (bf16_src, round(pairs)),

@@ -36,8 +36,10 @@ def test_sharded_computeM_equals_single_gpu_world2():
     if _gpu_count() < 2:
         pytest.skip("needs 2 GPUs")
     # small thresholds so that the 900-cell problem exercises every split path
+    # MGPU_EIG_N = 1500: the collective eigensolver test crosses several 128-row ownership groups, panels that start
+    # on odd and even multiples of 64 (lead rows of the sharded trailing update) and the small-block tail
     rows = _run(2, 900, 400, dict(RSOPTSC_SPLIT_MIN_N="150", RSOPTSC_STEDC_SPLIT_MIN="128", RSOPTSC_SYTRD_MG_MIN_N="128",
-                                  RSOPTSC_GEMM_MIN="0"), 29541)
+                                  RSOPTSC_GEMM_MIN="0", MGPU_EIG_N="1500"), 29541)
     for r in rows:
         assert r["relZ"] < 1e-10 and r["collectives"] > 0
     assert "relZ_oracle" in [k for r in rows for k in r]

@@ -132,3 +132,27 @@ def test_mg_cyclic_map_tiles_every_column_once(mB, P):
             own, pref, lfirst = tabs[r]
             per.append(mg_F(pref, lfirst[Bmin], Bmin, len(own)))
         assert max(per) - min(per) <= 2 * SPT * (mB - Bmin + 1)
+
+
+# ---- panel gather of the sharded trailing update (comm.cu: cyc_rows_below / k_cyc_panel) ---------------------------
+def cyc_rows_below(x, group, P, q):
+    G, cyc, rem = x // group, (x // group) // P, (x // group) % P
+    return cyc * group + (group if rem > q else 0) + (x % group if rem == q else 0)
+
+
+@pytest.mark.parametrize("n,r0,P", [(1000, 0, 2), (1000, 64, 2), (1000, 448, 4), (5000, 1984, 8), (130, 128, 8), (700, 699, 3)])
+def test_cyclic_row_packing_is_a_bijection(n, r0, P):
+    group = 128
+    lmax = max(cyc_rows_below(n, group, P, q) - cyc_rows_below(r0, group, P, q) for q in range(P))
+    seen = {}
+    for i in range(r0, n):
+        q = (i // group) % P
+        idx = cyc_rows_below(i, group, P, q) - cyc_rows_below(r0, group, P, q)
+        assert 0 <= idx < lmax
+        assert (q, idx) not in seen                      # no two rows of a rank share a slot
+        seen[(q, idx)] = i
+    for q in range(P):                                    # the slots of a rank are dense and in row order
+        mine = sorted(idx for (qq, idx) in seen if qq == q)
+        assert mine == list(range(len(mine)))
+        rows = [seen[(q, k)] for k in mine]
+        assert rows == sorted(rows)
