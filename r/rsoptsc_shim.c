@@ -143,6 +143,31 @@ SEXP rsoptsc_R_nmf(SEXP V, SEXP k, SEXP max_iter) {
   return out;
 }
 
+/* .Call("rsoptsc_R_nmf_sweep", V, k_lo, k_hi, maxIter) -> list(labels = n x (k_hi - k_lo + 1) integer matrix, iters)
+ * the rank sweep of BASELINE.json configs[3] (sapply(k_lo:k_hi, function(k) ClusterCells(V, k)$labels) in the
+ * reference's terms), all ranks advanced together on the GPU */
+SEXP rsoptsc_R_nmf_sweep(SEXP V, SEXP k_lo, SEXP k_hi, SEXP max_iter) {
+  int64_t n, nc;
+  dims(V, &n, &nc);
+  if (n != nc) Rf_error("similarity matrix must be square");
+  const int lo = Rf_asInteger(k_lo), hi = Rf_asInteger(k_hi);
+  if (hi < lo) Rf_error("k_hi < k_lo");
+  const int R = hi - lo + 1;
+  /* the C ABI returns R x n row-major == n x R column-major: exactly R's layout of an n x R matrix */
+  SEXP lab = PROTECT(Rf_allocMatrix(INTSXP, (int)n, R));
+  SEXP its = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)R));
+  rsoptsc_set_progress(progress_cb, NULL);
+  int st = rsoptsc_nmf_sweep(REAL(V), n, lo, hi, Rf_asInteger(max_iter), (int32_t*)INTEGER(lab), (int32_t*)INTEGER(its));
+  rsoptsc_set_progress(NULL, NULL);
+  if (st != 0) { UNPROTECT(2); check(st); }
+  const char* nm[] = {"labels", "iters"};
+  SEXP out = PROTECT(named_list(2, nm));
+  SET_VECTOR_ELT(out, 0, lab);
+  SET_VECTOR_ELT(out, 1, its);
+  UNPROTECT(3);
+  return out;
+}
+
 /* .Call("rsoptsc_R_get_components", S, tol) -> list(val, n_eigs)   (R/Clustering.R:96-105) */
 SEXP rsoptsc_R_get_components(SEXP S, SEXP tol) {
   int64_t n, nc;
@@ -328,6 +353,7 @@ static const R_CallMethodDef call_methods[] = {
     {"rsoptsc_R_similarity", (DL_FUNC)&rsoptsc_R_similarity, 5},
     {"rsoptsc_R_computeM", (DL_FUNC)&rsoptsc_R_computeM, 3},
     {"rsoptsc_R_nmf", (DL_FUNC)&rsoptsc_R_nmf, 3},
+    {"rsoptsc_R_nmf_sweep", (DL_FUNC)&rsoptsc_R_nmf_sweep, 4},
     {"rsoptsc_R_get_ensemble", (DL_FUNC)&rsoptsc_R_get_ensemble, 5},
     {"rsoptsc_R_get_consensus", (DL_FUNC)&rsoptsc_R_get_consensus, 1},
     {"rsoptsc_R_log_normalize", (DL_FUNC)&rsoptsc_R_log_normalize, 3},
