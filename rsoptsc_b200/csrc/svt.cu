@@ -137,8 +137,12 @@ void svt_small_batch(const std::vector<double*>& blocks, const std::vector<int64
   std::vector<SmallJob> jobs(nb);
   {
     Phase ph("svt_small_eig");
-    cudaEvent_t ready;
-    RS_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    struct EventGuard {
+      cudaEvent_t e = nullptr;
+      ~EventGuard() { if (e) cudaEventDestroy(e); }
+    } ready_guard;
+    RS_CUDA(cudaEventCreateWithFlags(&ready_guard.e, cudaEventDisableTiming));
+    const cudaEvent_t ready = ready_guard.e;
     RS_CUDA(cudaEventRecord(ready, c.stream));  // the blocks of A are complete on the library stream
     // buffers first, on this thread (the caching allocator is not thread-safe)
     std::vector<size_t> wdev(nb, 0), whost(nb, 0);
@@ -170,6 +174,8 @@ void svt_small_batch(const std::vector<double*>& blocks, const std::vector<int64
         }
       } catch (const std::exception& e) {
         *err = e.what();
+      } catch (...) {
+        *err = "unknown error";
       }
     };
     std::string err0, err1;
@@ -181,7 +187,6 @@ void svt_small_batch(const std::vector<double*>& blocks, const std::vector<int64
       RS_CUDA(cudaEventRecord(lanes[l].done, lanes[l].stream));
       RS_CUDA(cudaStreamWaitEvent(c.stream, lanes[l].done, 0));  // join: the library stream continues after both lanes
     }
-    cudaEventDestroy(ready);
   }
   DevBuf<double> T, B;
   for (size_t i = 0; i < nb; ++i) {

@@ -118,3 +118,32 @@ def test_host_tridiag_bisect(lib):
             ref = eigvalsh_tridiagonal(d, e[:k - 1]) if k > 1 else d.copy()
             assert np.all(np.diff(lam) >= 0)
             assert np.abs(lam - ref).max() <= 5e-14 * max(np.abs(ref).max(), 1e-300), (k, kind)
+
+
+def test_r_wrapper_calls_match_the_shim_registration():
+    """Every .Call("name", ...) in r/RSoptSC_b200.R names a routine registered in r/rsoptsc_shim.c with the same number
+    of arguments (R checks this at run time with .registration = TRUE; R is not available here)."""
+    shim = open(os.path.join(ROOT, "r", "rsoptsc_shim.c")).read()
+    reg = {m.group(1): int(m.group(2)) for m in re.finditer(r'\{"(rsoptsc_R_\w+)",\s*\(DL_FUNC\)&\w+,\s*(\d+)\}', shim)}
+    assert len(reg) >= 15
+    for name in reg:                                       # registered routines exist with that arity
+        sig = re.search(r"SEXP %s\(([^)]*)\)" % name, shim)
+        assert sig, name
+        args = [a for a in sig.group(1).split(",") if a.strip() and a.strip() != "void"]
+        assert len(args) == reg[name], name
+    rsrc = open(os.path.join(ROOT, "r", "RSoptSC_b200.R")).read()
+    rsrc = re.sub(r"#.*", "", rsrc)
+    calls = list(re.finditer(r'\.Call\("(rsoptsc_R_\w+)"', rsrc))
+    assert len(calls) >= 8
+    for m in calls:
+        name = m.group(1)
+        assert name in reg, name
+        # count top-level commas of this .Call(...)
+        i, depth, commas = m.end(), 1, 0
+        while depth > 0:
+            ch = rsrc[i]
+            depth += ch in "([{"
+            depth -= ch in ")]}"
+            commas += (ch == "," and depth == 1)
+            i += 1
+        assert commas == reg[name], (name, commas, reg[name])
