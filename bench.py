@@ -127,7 +127,7 @@ def bench_config(args, world):
             "nmf_rank": RANK, "parallelism": par,
             "headline_config_measured": args.cells >= 50000,
             "headline_note": ("BASELINE.json's metric is quoted at 50,000 cells (configs[2]); one step of it takes 443 s "
-                              "on one B200, 161 s on 4 and 102 s on 8 (profiles/r2_bench_50k_*gpu.json, this same code with "
+                              "on one B200, 296 s on 2, 161 s on 4 and 102 s on 8 (profiles/r2_bench_50k_*gpu.json, this same code with "
                               "`--cells 50000 --steps 1 --warmup 0`), so the driver-sized run (--steps 20) uses configs[1]"),
             "l2": "working set (%.1f GB of dense n x n state) exceeds the 126 MB L2" % (5 * 8e-9 * args.cells * args.cells)}
 

@@ -156,3 +156,31 @@ def test_cyclic_row_packing_is_a_bijection(n, r0, P):
         assert mine == list(range(len(mine)))
         rows = [seen[(q, k)] for k in mine]
         assert rows == sorted(rows)
+
+
+# ---- sharded trailing update (gemm_ozaki.cu: ozaki_syr2k_lower_sub) vs kernel ownership (sytrd_mg.cuh) ---------------
+@pytest.mark.parametrize("n,P", [(700, 2), (1500, 2), (2700, 4), (7954, 8), (4097, 3)])
+def test_sharded_update_rows_cover_what_the_kernel_reads(n, P):
+    """For every panel start r0 (multiples of 64) the 128-row tile rows a rank updates are exactly the block rows the
+    panel kernel lets it read (owner of 64-row block row I = (I // 2) % P), and every trailing row has one updater."""
+    BM, TILE = 128, 64
+    for r0 in range(64, n, 64):
+        nr = n - r0
+        if nr < 384:                      # small tail: every rank updates everything
+            continue
+        lead = r0 % BM
+        rows = nr + lead
+        g0 = (r0 - lead) // BM
+        ntile = (rows + BM - 1) // BM
+        updater = {}
+        for rank in range(P):
+            for i in range(ntile):
+                if (g0 + i) % P != rank:
+                    continue
+                for row in range(r0 - lead + i * BM, min(r0 - lead + (i + 1) * BM, n)):
+                    if row >= r0:
+                        assert row not in updater
+                        updater[row] = rank
+        assert sorted(updater) == list(range(r0, n))
+        for row, rank in updater.items():
+            assert ((row // TILE) >> 1) % P == rank
