@@ -101,14 +101,20 @@ def cpu_oracle_sample(data, cells, steps=1, threads=None):
     return times
 
 
-def best_cpu_threads(data, cells=300):
-    """torchrun pins OMP_NUM_THREADS=1 and an oversubscribed OpenBLAS can be slower than a few threads:
-    a short probe (300 cells) picks the BLAS thread count among {all, half, 8, 1} host threads."""
+def best_cpu_threads(data, cells=500):
+    """BLAS thread count for the CPU arm.  torchrun pins OMP_NUM_THREADS=1 and an oversubscribed OpenBLAS can be slower
+    than a few threads, so a short probe at 500 cells (large enough for the threaded LAPACK paths to matter: a
+    300-cell probe picked 1 thread on a 16-CPU box where 8 threads are 1.9x faster at 1,000 cells) times the multi-thread
+    candidates {all, half, 8} host CPUs; a single thread is only a candidate on a single-CPU host."""
     ncpu = os.cpu_count() or 1
-    cand = sorted({1, min(8, ncpu), max(1, ncpu // 2), ncpu}, reverse=True)
+    cand = sorted({min(8, ncpu), max(1, ncpu // 2), ncpu}, reverse=True)
+    if ncpu >= 2:
+        cand = [c for c in cand if c >= 2]
+    cells = min(cells, data.shape[1])
+    cpu_oracle_sample(data, min(cells, 200), steps=1, threads=cand[0])      # page-in / thread-pool warm-up
     best = None
     for th in cand:
-        t = min(cpu_oracle_sample(data, cells, steps=2, threads=th))
+        t = min(cpu_oracle_sample(data, cells, steps=1, threads=th))
         if best is None or t < best[1]:
             best = (th, t)
     return best
@@ -141,12 +147,12 @@ def run_reference(args, rank, world):
         return
     from rsoptsc_b200.synthetic import synthetic_lognorm
     data, _ = synthetic_lognorm(args.genes, 2000, seed=0)
-    threads, t300 = best_cpu_threads(data)          # doubles as BLAS warm-up
+    threads, t500 = best_cpu_threads(data)          # doubles as BLAS warm-up
     cells = args.cpu_cells
     if not args.cpu_cells_fixed:
         for cand in (1000, 700, 500):
             cells = cand
-            if args.steps * t300 * (cand / 300.0) ** 2.6 <= 360.0:
+            if args.steps * t500 * (cand / 500.0) ** 2.6 <= 360.0:
                 break
     for _ in range(min(args.warmup, 1)):            # warm-up steps: one short pass (page-in, thread pool)
         cpu_oracle_sample(data, min(cells, 300), threads=threads)
@@ -397,7 +403,7 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             sdata = data if n >= 300 else synthetic_lognorm(m, 300, seed=0)[0]
-            cpu_threads, _ = best_cpu_threads(sdata, min(300, n))
+            cpu_threads, _ = best_cpu_threads(sdata, min(500, n))
             nc = min(args.cpu_cells, n)
             t_cpu = cpu_oracle_sample(data, nc, threads=cpu_threads)[0]
             cpu = {"value": nc / t_cpu, "unit": UNIT, "cores": cpu_threads, "host_cpus": os.cpu_count(), "kind": "port",
