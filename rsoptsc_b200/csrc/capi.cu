@@ -65,13 +65,27 @@ static size_t bucket_of(size_t bytes) {
   const size_t step = (size_t)1 << (hb - 3);
   return (bytes + step - 1) / step * step;
 }
+// Blocks remember the bucket they were allocated with: a request may be served by a cached block of a LARGER bucket
+// (big requests only, at most 1.5x), so that a sequence of slowly shrinking multi-GB requests -- the int8 slice buffer
+// of the Z panel in the back-transformation, one size per 1,024-reflector block -- reuses one block instead of going
+// through cudaMalloc / cudaFree for every new size.
+static std::unordered_map<void*, size_t>& block_sizes() {
+  static auto* m = new std::unordered_map<void*, size_t>();
+  return *m;
+}
+static constexpr size_t POOL_FUZZY_MIN = (size_t)64 << 20;
 void* pool_alloc(size_t bytes) {
   const size_t b = bucket_of(bytes);
   auto it = g_pool.find(b);
+  if ((it == g_pool.end() || it->second.empty()) && b >= POOL_FUZZY_MIN) {
+    for (it = g_pool.lower_bound(b); it != g_pool.end() && it->first <= b + b / 2; ++it)
+      if (!it->second.empty()) break;
+    if (it != g_pool.end() && it->first > b + b / 2) it = g_pool.end();
+  }
   if (it != g_pool.end() && !it->second.empty()) {
     void* p = it->second.back();
     it->second.pop_back();
-    g_pooled_bytes -= std::min(g_pooled_bytes, b);
+    g_pooled_bytes -= std::min(g_pooled_bytes, it->first);
     return p;
   }
   void* p = nullptr;
@@ -83,6 +97,7 @@ void* pool_alloc(size_t bytes) {
   }
   if (e != cudaSuccess)
     fail(2, __FILE__, __LINE__, std::string("CUDA: cudaMalloc of ") + std::to_string(b) + " bytes failed: " + cudaGetErrorString(e));
+  block_sizes()[p] = b;
   return p;
 }
 static size_t pool_limit() {                       // idle bytes above which the cache is handed back
@@ -95,14 +110,18 @@ static size_t pool_limit() {                       // idle bytes above which the
 }
 void pool_free(void* p, size_t bytes) {
   if (!p) return;
-  const size_t b = bucket_of(bytes);
+  auto known = block_sizes().find(p);
+  const size_t b = known != block_sizes().end() ? known->second : bucket_of(bytes);  // the block's own bucket
   g_pool[b].push_back(p);
   g_pooled_bytes += b;
   if (g_pooled_bytes > pool_limit()) pool_trim();
 }
 void pool_trim() {
   for (auto& kv : g_pool)
-    for (void* p : kv.second) cudaFree(p);
+    for (void* p : kv.second) {
+      cudaFree(p);
+      block_sizes().erase(p);
+    }
   g_pool.clear();
   g_pooled_bytes = 0;
 }
