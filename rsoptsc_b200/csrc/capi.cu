@@ -131,7 +131,6 @@ struct PhaseRec { double ms = 0; int64_t calls = 0; std::vector<std::pair<cudaEv
 static std::vector<std::string> g_phase_names;
 static std::vector<PhaseRec> g_phases;
 static bool g_timers_on = false;
-static int g_phase_depth = 0;
 
 static int phase_id(const char* name) {
   for (size_t i = 0; i < g_phase_names.size(); ++i)

@@ -187,7 +187,7 @@ static bool pca_scores_sparse(const Compressed& csr, const Compressed& csc, int6
 // eigenvalue 1 of M is simple) a Lanczos process with full reorthogonalisation on the sparse M finds the top of the
 // spectrum; a second, deflated run certifies that no copy of a multiple eigenvalue was missed.  Components
 // too small to bother (or a run that cannot be certified) go through the dense values-only eigensolver.
-__global__ void k_scale_by(double* __restrict__ y, const double* __restrict__ x, const double* __restrict__ dd, int64_t n) {
+__global__ void k_scale_by(double* y, const double* x, const double* __restrict__ dd, int64_t n) {  // y may alias x
   const int64_t i = (int64_t)blockIdx.x * ET + threadIdx.x;
   if (i < n) y[i] = x[i] * dd[i];
 }
