@@ -147,7 +147,7 @@ def run_reference(args, rank, world):
         return
     from rsoptsc_b200.synthetic import synthetic_lognorm
     data, _ = synthetic_lognorm(args.genes, 2000, seed=0)
-    threads, t500 = best_cpu_threads(data)          # doubles as BLAS warm-up
+    threads, t500 = best_cpu_threads(data, min(500, args.cpu_cells) if args.cpu_cells_fixed else 500)  # + BLAS warm-up
     cells = args.cpu_cells
     if not args.cpu_cells_fixed:
         for cand in (1000, 700, 500):
