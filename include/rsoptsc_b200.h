@@ -280,6 +280,13 @@ int32_t rsoptsc_host_choose_K(const double* eig, int64_t len);
  * may be NULL. */
 int rsoptsc_host_shard_owner(const int32_t* idx, int64_t n, int32_t K, int32_t nranks, int64_t split_min,
                              int32_t* owner, int32_t* component, int32_t* split);
+/* Ownership tables of the fused multi-GPU tridiagonalisation (sytrd_mg.cuh; no GPU needed): the trailing matrix of an
+ * n-row block is owned in 128-row groups dealt cyclically, 64-row block row I belongs to rank (I / 2) mod nranks.  For
+ * `rank`: ownI (capacity ceil(n/64)) its block rows ascending, *nl their count, pref (capacity ceil(n/64) + 1) the strip
+ * prefix sums, lfirst (capacity ceil(n/64) + 1) first own block row at or below every block row.  Used by the CPU
+ * test of the kernel's unit map. */
+int rsoptsc_host_mg_tables(int64_t n, int32_t nranks, int32_t rank, int32_t* ownI, int32_t* nl, int64_t* pref,
+                           int32_t* lfirst);
 
 #ifdef __cplusplus
 }

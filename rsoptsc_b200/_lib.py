@@ -89,6 +89,7 @@ SIGNATURES = {
     "rsoptsc_host_tridiag_eig": (C.c_int, [C.c_int32, c_double_p, c_double_p, c_double_p]),
     "rsoptsc_host_tridiag_bisect": (C.c_int, [C.c_int32, c_double_p, c_double_p, c_double_p]),
     "rsoptsc_host_choose_K": (C.c_int32, [c_double_p, C.c_int64]),
+    "rsoptsc_host_mg_tables": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, c_int32_p, c_int32_p, c_int64_p, c_int32_p]),
     "rsoptsc_host_shard_owner": (C.c_int, [c_int32_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, c_int32_p, c_int32_p,
                                            c_int32_p]),
 }

@@ -15,6 +15,8 @@ std::atomic<int64_t> g_launches{0};
 static Context g_ctx;
 static thread_local std::string g_err;
 void release_dense_scratch();  // dense.cu
+void sytrd_mg_tables_host(int64_t n, int nranks, int rank, std::vector<int>& ownI, std::vector<long long>& pref,
+                          std::vector<int>& lfirst);  // sytrd_mg.cu
 
 void ensure_init(int dev);
 Context& ctx() {
@@ -880,6 +882,19 @@ int rsoptsc_host_tridiag_eig(int32_t k, double* d, const double* e, double* V) {
     tridiag_eig(dd, ee, V ? &vv : nullptr);
     std::memcpy(d, dd.data(), sizeof(double) * k);
     if (V) std::memcpy(V, vv.data(), sizeof(double) * (size_t)k * k);
+  });
+}
+int rsoptsc_host_mg_tables(int64_t n, int32_t nranks, int32_t rank, int32_t* ownI, int32_t* nl, int64_t* pref, int32_t* lfirst) {
+  return guarded([&] {
+    RS_REQUIRE(n >= 1 && n <= 65535 && nranks >= 1 && nranks <= MAX_RANKS && rank >= 0 && rank < nranks,
+               "host_mg_tables: bad arguments");
+    std::vector<int> o, l;
+    std::vector<long long> p;
+    sytrd_mg_tables_host(n, nranks, rank, o, p, l);
+    if (nl) *nl = (int32_t)o.size();
+    if (ownI) std::copy(o.begin(), o.end(), ownI);
+    if (pref) std::copy(p.begin(), p.end(), pref);
+    if (lfirst) std::copy(l.begin(), l.end(), lfirst);
   });
 }
 int rsoptsc_host_shard_owner(const int32_t* idx, int64_t n, int32_t K, int32_t nranks, int64_t split_min,

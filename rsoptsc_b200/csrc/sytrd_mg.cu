@@ -20,6 +20,11 @@ static int64_t mg_min_n() {
   return t;
 }
 
+void sytrd_mg_tables_host(int64_t n, int nranks, int rank, std::vector<int>& ownI, std::vector<long long>& pref,
+                          std::vector<int>& lfirst) {
+  sytrd::mg_tables_host(n, nranks, rank, ownI, pref, lfirst);
+}
+
 bool sytrd_mg_available(int64_t n) {
   if (!sharded() || n < mg_min_n() || comm().nranks > sytrd::MG_MAX_RANKS) return false;
   const char* off = getenv("RSOPTSC_SYTRD_MG");

@@ -501,18 +501,28 @@ inline size_t mg_tab_bytes(int64_t n) {
   const size_t mB = (size_t)((n + TILE - 1) / TILE);
   return (mB + 2) * sizeof(long long) + (2 * mB + 4) * sizeof(int);
 }
-inline cudaError_t mg_build_tab(int64_t n, int nranks, int rank, void* buf, cudaStream_t stream, MgTab* tab) {
+// the three tables of one rank on the host (shared with the CPU test of the map, rsoptsc_host_mg_tables)
+inline void mg_tables_host(int64_t n, int nranks, int rank, std::vector<int>& ownI, std::vector<long long>& pref,
+                           std::vector<int>& lfirst) {
   const int mB = (int)((n + TILE - 1) / TILE);
-  std::vector<int> ownI, lfirst(mB + 1);
+  ownI.clear();
+  lfirst.assign(mB + 1, 0);
   for (int I = 0; I < mB; ++I)
     if (mg_owner_of_block_row(I, nranks) == rank) ownI.push_back(I);
   const int nl = (int)ownI.size();
-  std::vector<long long> pref(nl + 1, 0);
+  pref.assign(nl + 1, 0);
   for (int l = 0; l < nl; ++l) pref[l + 1] = pref[l] + (long long)SPT * (ownI[l] + 1);
   for (int I = 0, l = 0; I <= mB; ++I) {
     while (l < nl && ownI[l] < I) ++l;
     lfirst[I] = l;
   }
+}
+inline cudaError_t mg_build_tab(int64_t n, int nranks, int rank, void* buf, cudaStream_t stream, MgTab* tab) {
+  const int mB = (int)((n + TILE - 1) / TILE);
+  std::vector<int> ownI, lfirst;
+  std::vector<long long> pref;
+  mg_tables_host(n, nranks, rank, ownI, pref, lfirst);
+  const int nl = (int)ownI.size();
   char* p = static_cast<char*>(buf);
   long long* d_pref = reinterpret_cast<long long*>(p);
   int* d_own = reinterpret_cast<int*>(p + (size_t)(mB + 2) * sizeof(long long));

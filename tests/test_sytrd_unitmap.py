@@ -184,3 +184,28 @@ def test_sharded_update_rows_cover_what_the_kernel_reads(n, P):
         assert sorted(updater) == list(range(r0, n))
         for row, rank in updater.items():
             assert ((row // TILE) >> 1) % P == rank
+
+
+@pytest.mark.parametrize("n,P", [(64, 2), (700, 2), (2700, 4), (7954, 8), (65535, 8), (4097, 3)])
+def test_library_mg_tables_equal_the_restatement(n, P):
+    """The C++ table builder of the kernel (sytrd_mg.cuh: mg_tables_host, through rsoptsc_host_mg_tables; no GPU needed)
+    against mg_tables above, which the map tests of this file are written on."""
+    import ctypes as C
+
+    import numpy as np
+    from rsoptsc_b200 import _lib
+    lib = _lib.load()
+    mB = (n + 63) // 64
+    for rank in range(P):
+        own = np.zeros(mB, dtype=np.int32)
+        pref = np.zeros(mB + 1, dtype=np.int64)
+        lfirst = np.zeros(mB + 1, dtype=np.int32)
+        nl = C.c_int32(0)
+        st = lib.rsoptsc_host_mg_tables(n, P, rank, own.ctypes.data_as(_lib.c_int32_p), C.byref(nl),
+                                        pref.ctypes.data_as(_lib.c_int64_p), lfirst.ctypes.data_as(_lib.c_int32_p))
+        assert st == 0, lib.rsoptsc_last_error()
+        o, p, lf = mg_tables(mB, P, rank)
+        assert nl.value == len(o)
+        assert own[:nl.value].tolist() == o
+        assert pref[:nl.value + 1].tolist() == p
+        assert lfirst.tolist() == lf
